@@ -1,0 +1,279 @@
+"""Host-side mirror of the reference's public surface: `track(file; …)`,
+`track(files; …)`, and the start-up helpers (src/PawsomeTracker.jl:64-214),
+with the Tracker's arithmetic routed to libpawsome_cuda.so.
+
+What is kept verbatim: keyword names and defaults, the three `start_location`
+forms, window-size conventions, the timestamp construction, segment chaining.
+What is different by necessity: there is no ffmpeg/VideoIO in this image, so a
+"file" is any object implementing the small `VideoSource` protocol below
+(`SyntheticVideo`, `ArrayVideo`, or `CvVideo` for real files through OpenCV).
+`missing` is spelled `None`; `CartesianIndex(i, j)` is the class below.
+"""
+from __future__ import annotations
+
+from fractions import Fraction
+from typing import NamedTuple, Sequence
+
+import numpy as np
+
+from .tracker import Tracker, TrackerBatch, fix_window_size, guess_window_size
+
+DEFAULT_MAX_DURATION_SECONDS = 86399.999  # src/PawsomeTracker.jl:19
+
+
+class CartesianIndex(NamedTuple):
+    """1-based (row, col) into the raw stored frame (src/PawsomeTracker.jl:118)."""
+    i: int
+    j: int
+
+
+# ---------------------------------------------------------------------------
+# video sources (the decode side stays on the host — BASELINE.json north_star)
+# ---------------------------------------------------------------------------
+class ArrayVideo:
+    """Frames already in host memory: a (T, H, W) array or a list of HxW arrays."""
+
+    def __init__(self, frames, fps: float = 24.0, sar=1):
+        self.frames = frames
+        self.fps = float(fps)
+        self.sar = Fraction(sar)
+
+    def __len__(self):
+        return len(self.frames)
+
+    def frame(self, k: int, out=None):
+        f = self.frames[k]
+        if out is None:
+            return np.array(f, copy=True)
+        np.copyto(out, f)
+        return out
+
+
+class CvVideo:
+    """A real video file decoded on the host with OpenCV's FFmpeg backend to
+    GRAY8 (the role of `openvideo(…, target_format = AV_PIX_FMT_GRAY8)`,
+    src/PawsomeTracker.jl:157)."""
+
+    def __init__(self, path: str):
+        import cv2  # host decode only
+        self._cv2 = cv2
+        self.cap = cv2.VideoCapture(path)
+        if not self.cap.isOpened():
+            raise FileNotFoundError(path)
+        self.fps = float(self.cap.get(cv2.CAP_PROP_FPS)) or 24.0
+        num = self.cap.get(cv2.CAP_PROP_SAR_NUM) or 1
+        den = self.cap.get(cv2.CAP_PROP_SAR_DEN) or 1
+        self.sar = Fraction(int(num), int(den)) if num > 0 and den > 0 else Fraction(1)
+        self._n = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        self._next = 0
+
+    def __len__(self):
+        return self._n
+
+    def frame(self, k: int, out=None):
+        if k != self._next:
+            self.cap.set(self._cv2.CAP_PROP_POS_FRAMES, k)
+        ok, bgr = self.cap.read()
+        if not ok:
+            raise EOFError
+        self._next = k + 1
+        g = self._cv2.cvtColor(bgr, self._cv2.COLOR_BGR2GRAY)
+        if out is None:
+            return g
+        np.copyto(out, g)
+        return out
+
+
+def open_video(file):
+    if isinstance(file, str):
+        return CvVideo(file)
+    if hasattr(file, "frame") and hasattr(file, "fps"):
+        return file
+    raise TypeError("file must be a path or a VideoSource (SyntheticVideo / ArrayVideo / CvVideo)")
+
+
+def aspect_ratio(vid) -> Fraction:
+    """VideoIO.aspect_ratio(vid) — used at src/PawsomeTracker.jl:80."""
+    return Fraction(getattr(vid, "sar", 1))
+
+
+class _Resampled:
+    """`ffmpeg -ss start -i file -t t -vf fps=fps` (src/PawsomeTracker.jl:155):
+    output frame k shows the source frame nearest to time start + k/fps; the
+    stream ends after round(t·fps) frames or at the end of the source."""
+
+    def __init__(self, vid, start: float, t: float, fps: float):
+        self.vid, self.start, self.fps = vid, float(start), float(fps)
+        self.limit = int(round(float(t) * float(fps)))
+        self.k = 0
+
+    def _src_index(self, k: int) -> int:
+        return int(np.floor((self.start + k / self.fps) * self.vid.fps + 0.5))
+
+    def eof(self) -> bool:
+        return self.k >= self.limit or self._src_index(self.k) >= len(self.vid)
+
+    def read(self, out=None):
+        if self.eof():
+            raise EOFError
+        f = self.vid.frame(self._src_index(self.k), out)
+        self.k += 1
+        return f
+
+
+# ---------------------------------------------------------------------------
+# start-up helpers
+# ---------------------------------------------------------------------------
+def get_guess(start_location, vid, img):
+    """src/PawsomeTracker.jl:74-90"""
+    if start_location is None:                                   # ::Missing  (:86-90)
+        return (img.shape[0] // 2, img.shape[1] // 2)
+    if isinstance(start_location, CartesianIndex):              # (:74-77)
+        return (int(start_location.i), int(start_location.j))
+    x, y = start_location                                       # (x, y) displayed px (:79-84)
+    sar = aspect_ratio(vid)
+    return (int(y), int(round(Fraction(int(x)) / sar)))          # round(Rational): ties to even, as Julia
+
+
+def get_start_ij_and_tracker(start_location, vid, img, target_width, window_size, darker_target, device=0):
+    """src/PawsomeTracker.jl:92-107"""
+    guess = get_guess(start_location, vid, img)
+    if start_location is None:
+        sz = img.shape
+        window_size2 = (sz[0] // 4, sz[1] // 4)                 # "this greatly affects processing time!" (:102)
+        trckr = Tracker(img, target_width, window_size2, darker_target, device)   # auto-detection pass (:103)
+        ij = trckr(guess)
+        trckr.close()
+        trckr = Tracker(img, target_width, window_size, darker_target, device)    # (:105)
+        return trckr, ij
+    trckr = Tracker(img, target_width, window_size, darker_target, device)
+    ij = trckr(guess)                                           # the first frame is refined, not trusted (:95)
+    return trckr, ij
+
+
+def track_one(file, start, stop, target_width, start_location, window_size, darker_target, fps, dia=None, device=0):
+    """src/PawsomeTracker.jl:148-174 with the intended loop body (:162, :167):
+    `while !eof(vid) && last_frame < n`, `indices[k] = trckr(indices[k-1])`."""
+    t = stop - start
+    n = int(round(fps * t))
+    ts = np.linspace(start, stop, n)                            # range(start, stop, n) (:152)
+    vid = _Resampled(open_video(file), start, t, fps)
+    img = vid.read()
+    trckr, ij = get_start_ij_and_tracker(start_location, vid.vid, img, target_width, window_size, darker_target, device)
+    indices = [ij]
+    try:
+        while not vid.eof() and len(indices) < n:
+            vid.read(out=trckr.img)                             # read!(vid, trckr.img.data) (:166)
+            indices.append(trckr(indices[-1]))                  # (:167)
+    finally:
+        trckr.close()
+    last = len(indices)
+    return ts[:last], np.asarray(indices, np.int64).reshape(last, 2)
+
+
+# ---------------------------------------------------------------------------
+# public API
+# ---------------------------------------------------------------------------
+def _no_diagnostics(diagnostic_file):
+    if diagnostic_file is not None:
+        raise NotImplementedError("diagnostic_file: the diagnostics video (src/diagnose.jl) is outside the "
+                                  "hot-path scope of this build (SURVEY §8f rank 4)")
+
+
+def track(file, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, target_width=25, start_location=None,
+          window_size=None, darker_target=True, fps=24, diagnostic_file=None, device=0):
+    """`track(file; …)` (src/PawsomeTracker.jl:130-146) or, when `file` is a list,
+    the segmented `track(files; …)` (:181-214).  Returns (ts, ij) with ij an
+    (n, 2) array of 1-based (row, col)."""
+    if isinstance(file, (list, tuple)):
+        return track_segments(file, start=start, stop=stop, target_width=target_width,
+                              start_location=start_location, window_size=window_size,
+                              darker_target=darker_target, fps=fps, diagnostic_file=diagnostic_file, device=device)
+    _no_diagnostics(diagnostic_file)
+    if window_size is None:
+        window_size = guess_window_size(target_width)
+    window_size = fix_window_size(window_size)
+    return track_one(file, start, stop, target_width, start_location, window_size, darker_target, fps, None, device)
+
+
+def track_segments(files: Sequence, *, start=None, stop=None, target_width=25, start_location=None,
+                   window_size=None, darker_target=True, fps=24, diagnostic_file=None, device=0):
+    """`track(files::AbstractVector; …)` — src/PawsomeTracker.jl:181-214."""
+    _no_diagnostics(diagnostic_file)
+    nfiles = len(files)
+    start = [0.0] * nfiles if start is None or np.isscalar(start) and start == 0 else list(start)
+    stop = ([DEFAULT_MAX_DURATION_SECONDS] * nfiles
+            if stop is None or np.isscalar(stop) and stop == DEFAULT_MAX_DURATION_SECONDS else list(stop))
+    start_location = [None] * nfiles if start_location is None else list(start_location)
+    if not (nfiles == len(start) == len(stop) == len(start_location)):            # @assert (:193)
+        raise AssertionError(f"Array length mismatch: files={nfiles}, start={len(start)}, stop={len(stop)}, "
+                             f"start_location={len(start_location)}")
+    if window_size is None:
+        window_size = guess_window_size(target_width)
+    window_size = fix_window_size(window_size)
+    tss, ijs = [], []
+    end_location = None
+    for f, t_start, t_stop, loc in zip(files, start, stop, start_location):
+        loc = loc if loc is not None else end_location                            # coalesce (:204)
+        ts_i, ij_i = track_one(f, t_start, t_stop, target_width, loc, window_size, darker_target, fps, None, device)
+        tss.append(ts_i)
+        ijs.append(ij_i)
+        end_location = CartesianIndex(int(ij_i[-1, 0]), int(ij_i[-1, 1]))         # (:206)
+    n = sum(len(t) for t in tss)
+    step = (tss[0][1] - tss[0][0]) if len(tss[0]) > 1 else 0.0
+    ts = tss[0][0] + step * np.arange(n)                                          # range(first, step=…, length=n) (:210)
+    return ts, np.concatenate(ijs, axis=0)
+
+
+def track_batch(files: Sequence, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, target_width=25,
+                start_location=None, window_size=None, darker_target=True, fps=24, device=0,
+                chunk_steps: int = 32):
+    """Batched counterpart with no equivalent in the reference: `track` over
+    many independent videos of identical geometry advanced in lock-step, one
+    CTA group per (video, window) per launch.  Per-video results are identical
+    to calling `track` on each video.  start_location: None, one location, or
+    one per video."""
+    nv = len(files)
+    if window_size is None:
+        window_size = guess_window_size(target_width)
+    window_size = fix_window_size(window_size)
+    locs = list(start_location) if isinstance(start_location, list) else [start_location] * nv
+    t = stop - start
+    n = int(round(fps * t))
+    ts = np.linspace(start, stop, n)
+    vids = [_Resampled(open_video(f), start, t, fps) for f in files]
+    first = [v.read() for v in vids]
+    H, W = first[0].shape
+    guess = np.array([get_guess(loc, v.vid, img) for loc, v, img in zip(locs, vids, first)], np.int32)
+    batch = TrackerBatch(nv, (H, W), target_width, window_size, darker_target, dtype=first[0].dtype, device=device)
+    try:
+        batch.set_frames(first)
+        batch.compute_fill()                                   # mode of each video's first frame (:47)
+        missing = np.array([loc is None for loc in locs])
+        ij0 = np.empty((nv, 2), np.int32)
+        if missing.any():                                      # auto-detect window size .÷ 4 (:102-104)
+            batch.set_window((H // 4, W // 4))
+            out, _ = batch.step(guess)
+            ij0[missing] = out[missing]
+            batch.set_window(window_size)
+        if (~missing).any():
+            out, _ = batch.step(guess)
+            ij0[~missing] = out[~missing]
+        batch.set_guess(ij0)
+        out_all = [ij0[None]]
+        count = 1
+        while count < n and not any(v.eof() for v in vids):
+            steps = []
+            for _ in range(min(chunk_steps, n - count)):
+                if any(v.eof() for v in vids):
+                    break
+                steps.append([v.read() for v in vids])
+            if not steps:
+                break
+            ij, _ = batch.track_host(steps, mode="footprint")
+            out_all.append(ij)
+            count += len(steps)
+        ij = np.concatenate(out_all, axis=0).astype(np.int64)  # (T, nv, 2)
+    finally:
+        batch.close()
+    return ts[:ij.shape[0]], ij

@@ -1,0 +1,908 @@
+// pt_api.cu — the C ABI of libpawsome_cuda.so (include/pawsome.h): handles,
+// HBM frame stores, pinned staging, streams, and the host-side loops that
+// drive the kernels.  No torch types, no CPU fallback: every compute entry
+// point launches CUDA kernels or fails.
+#include "../../include/pawsome.h"
+#include "pt_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(PT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+// ---- scalar arithmetic of the Tracker constructor (src/PawsomeTracker.jl:30,41-45)
+double sigma_of(double tw) { return tw / (2.0 * std::sqrt(2.0 * std::log(2.0))); }
+int kernel_len_of(double tw) { return 4 * (int)std::ceil(sigma_of(tw) * std::sqrt(2.0)) + 1; }
+
+void gaussian_factor(double sigma, int l, std::vector<double> &g)
+{
+    const int w = l / 2;
+    g.resize(l);
+    double s = 0.0;
+    for (int k = 0; k < l; ++k) {
+        const double x = (double)(k - w);
+        g[k] = std::exp(-(x * x) / (2.0 * sigma * sigma));
+        s += g[k];
+    }
+    for (int k = 0; k < l; ++k) g[k] /= s;
+}
+
+// FP32 taps exactly as the kernels consume them.  The row pass works on
+// (pixel − fill) in raw pixel units, so for u8 frames the N0f8 scale 1/255 is
+// folded into the row taps (in double, before rounding to float).
+void make_taps(double tw, bool darker, int pixel, std::vector<float> &rp, std::vector<float> &rm,
+               std::vector<float> &cp, std::vector<float> &cm)
+{
+    const int l = kernel_len_of(tw);
+    std::vector<double> gp, gm;
+    gaussian_factor(sigma_of(tw), l, gp);
+    gaussian_factor(sigma_of(tw) * std::sqrt(2.0), l, gm);
+    const double scale = pixel == PT_PIX_U8 ? 1.0 / 255.0 : 1.0;
+    const double dir = darker ? -1.0 : 1.0;
+    rp.resize(l); rm.resize(l); cp.resize(l); cm.resize(l);
+    for (int k = 0; k < l; ++k) {
+        rp[k] = (float)(gp[k] * scale);
+        rm[k] = (float)(gm[k] * scale);
+        cp[k] = (float)(dir * gp[k]);
+        cm[k] = (float)(-dir * gm[k]);
+    }
+}
+
+size_t px_size(int pixel) { return pixel == PT_PIX_U8 ? 1 : 4; }
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return PT_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        CU(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+        cap = bytes;
+        return PT_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return PT_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CU(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return PT_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+bool is_pinned_or_device(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+} // namespace
+
+// One worker of the footprint-streaming host loop: owns a contiguous slice of
+// the batch's videos, a stream, and pinned staging for crops and results.
+struct pt_lane {
+    cudaStream_t stream = nullptr;
+    PinnedBuf h_crops, h_res;
+    DevBuf d_crops;
+    int v0 = 0, v1 = 0;
+};
+
+struct pt_batch {
+    int n = 0, H = 0, W = 0;
+    double tw = 0;
+    int ws_r = 0, ws_c = 0, rr = 0, rc = 0, wr = 0, wc = 0;
+    int darker = 1, pixel = PT_PIX_U8, device = 0;
+    int L = 0, w = 0, Lpad = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    float2 *d_taps_row = nullptr, *d_taps_col = nullptr;
+    float *d_fill = nullptr;
+    int *d_fill_i = nullptr;
+    bool fill_set = false;
+    std::vector<int> h_fill;
+    int2 *d_guess = nullptr;
+    bool guess_set = false;
+    int2 *d_center = nullptr;            // crop-mode guess: centre of the footprint
+    unsigned long long *d_keys = nullptr;
+    unsigned int *d_counters = nullptr;
+    unsigned int *d_hist = nullptr;
+    int4 *d_pos = nullptr;
+    float *d_resp = nullptr;
+    // own HBM frame store (two slots so a whole-frame upload can overlap a step)
+    DevBuf d_frames[2];
+    size_t own_pitch = 0, own_stride = 0;
+    int cur_slot = 0;
+    bool have_frames = false;
+    // frames bound from caller-owned HBM
+    const void *bound_base = nullptr;
+    size_t bound_stride = 0, bound_pitch = 0;
+    // trajectory buffer for chained steps
+    DevBuf d_traj_pos, d_traj_resp, d_map;
+    PinnedBuf h_stage[2], h_out;
+    std::vector<pt_lane> lanes;
+    long long launches = 0;
+    bool use45 = false;
+};
+
+struct pt_tracker {
+    pt_batch *b = nullptr;
+};
+
+namespace {
+
+int set_device(const pt_batch *b) { CU(cudaSetDevice(b->device)); return PT_OK; }
+
+void configure_window(pt_batch *b, int ws_r, int ws_c)
+{
+    b->ws_r = ws_r; b->ws_c = ws_c;
+    b->rr = ws_r / 2; b->rc = ws_c / 2;           // radii = window_size .÷ 2 (:44)
+    b->wr = 2 * b->rr + 1; b->wc = 2 * b->rc + 1; // guess .- radii : guess .+ radii (:56)
+}
+
+// Fill the kernel argument block for one step.
+pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pitch, int H, int W,
+                      const int2 *guess, int nwin)
+{
+    pt::WinArgs a;
+    memset(&a, 0, sizeof a);
+    a.frames = frames; a.frame_stride = stride; a.pitch = (int)pitch; a.H = H; a.W = W;
+    a.fill = b->d_fill; a.guess = guess;
+    a.rect_mode = 0;
+    a.rr = b->rr; a.rc = b->rc; a.wr = b->wr; a.wc = b->wc;
+    a.L = b->L; a.w = b->w; a.Lpad = b->Lpad;
+    a.taps_row = b->d_taps_row; a.taps_col = b->d_taps_col;
+    a.keys = b->d_keys; a.counters = b->d_counters;
+    a.out_pos = b->d_pos; a.out_resp = b->d_resp;
+    a.next_guess = nullptr; a.traj_pos = nullptr; a.traj_resp = nullptr; a.map_out = nullptr;
+    (void)nwin;
+    return a;
+}
+
+void decompose(pt::WinArgs &a, int nwin)
+{
+    a.strips = (a.wc + pt::kTileCols - 1) / pt::kTileCols;
+    const int total = nwin * a.strips;
+    const int target = 2 * 148;
+    int chunks = 1;
+    if (total < target) {
+        chunks = (target + total - 1) / total;
+        const int maxc = (a.wr + pt::kBatchRows - 1) / pt::kBatchRows;
+        chunks = std::max(1, std::min(chunks, maxc));
+    }
+    a.CH = (a.wr + chunks - 1) / chunks;
+    a.chunks = (a.wr + a.CH - 1) / a.CH;
+}
+
+int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
+{
+    cudaError_t e;
+    if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a)) {
+        e = pt::launch_window45(a, nwin, b->pixel, s);
+    } else {
+        decompose(a, nwin);
+        e = pt::launch_generic(a, nwin, b->pixel, s);
+    }
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    b->launches += 1;
+    return PT_OK;
+}
+
+int current_frames(pt_batch *b, const void **base, size_t *stride, size_t *pitch)
+{
+    if (b->bound_base) { *base = b->bound_base; *stride = b->bound_stride; *pitch = b->bound_pitch; return PT_OK; }
+    if (b->have_frames) { *base = b->d_frames[b->cur_slot].p; *stride = b->own_stride; *pitch = b->own_pitch; return PT_OK; }
+    return fail(PT_ERR_STATE, "no frame attached: call pt_batch_set_frames or pt_batch_bind_device_frames first");
+}
+
+int upload_guess(pt_batch *b, const int32_t *g, cudaStream_t s)
+{
+    int rc = b->h_out.ensure((size_t)b->n * 32);
+    if (rc) return rc;
+    // staging region [n*16, n*24) of h_out is reserved for guesses
+    int32_t *st = reinterpret_cast<int32_t *>((char *)b->h_out.p + (size_t)b->n * 24);
+    CU(cudaStreamSynchronize(s)); // an earlier async copy may still be reading the staging
+    memcpy(st, g, sizeof(int32_t) * 2 * (size_t)b->n);
+    CU(cudaMemcpyAsync(b->d_guess, st, sizeof(int2) * (size_t)b->n, cudaMemcpyHostToDevice, s));
+    b->guess_set = true;
+    return PT_OK;
+}
+
+// Copy n host frames into d_frames[slot] on stream s, through pinned staging
+// unless the caller's memory is already page-locked.
+int upload_frames(pt_batch *b, const void *const *frames, size_t pitch, int slot, cudaStream_t s)
+{
+    const size_t es = px_size(b->pixel);
+    const size_t row_bytes = (size_t)b->W * es;
+    const size_t src_pitch_b = pitch * es;
+    if (pitch < (size_t)b->W) return fail(PT_ERR_ARG, "pitch %zu smaller than W %d", pitch, b->W);
+    int rc = b->d_frames[slot].ensure(b->own_stride * es * (size_t)b->n);
+    if (rc) return rc;
+    char *dbase = (char *)b->d_frames[slot].p;
+    const size_t dst_pitch_b = b->own_pitch * es, dst_stride_b = b->own_stride * es;
+    const bool pinned = is_pinned_or_device(frames[0]);
+    if (pinned) {
+        for (int v = 0; v < b->n; ++v)
+            CU(cudaMemcpy2DAsync(dbase + dst_stride_b * v, dst_pitch_b, frames[v], src_pitch_b, row_bytes,
+                                 (size_t)b->H, cudaMemcpyDefault, s));
+        return PT_OK;
+    }
+    // pageable source: pack rows into pinned staging (two halves, alternating) then DMA
+    const size_t frame_bytes = row_bytes * (size_t)b->H;
+    const size_t per_half = std::max<size_t>(1, std::min<size_t>((size_t)b->n, (64u << 20) / std::max<size_t>(frame_bytes, 1)));
+    for (int h = 0; h < 2; ++h) { rc = b->h_stage[h].ensure(per_half * frame_bytes); if (rc) return rc; }
+    int half = 0;
+    for (int v0 = 0; v0 < b->n; v0 += (int)per_half, half ^= 1) {
+        const int v1 = std::min(b->n, v0 + (int)per_half);
+        CU(cudaEventSynchronize(b->ev_copy[half])); // staging half free again?
+        char *st = (char *)b->h_stage[half].p;
+        for (int v = v0; v < v1; ++v) {
+            const char *src = (const char *)frames[v];
+            char *dst = st + (size_t)(v - v0) * frame_bytes;
+            if (src_pitch_b == row_bytes) memcpy(dst, src, frame_bytes);
+            else for (int y = 0; y < b->H; ++y) memcpy(dst + (size_t)y * row_bytes, src + (size_t)y * src_pitch_b, row_bytes);
+        }
+        for (int v = v0; v < v1; ++v)
+            CU(cudaMemcpy2DAsync(dbase + dst_stride_b * v, dst_pitch_b, st + (size_t)(v - v0) * frame_bytes,
+                                 row_bytes, row_bytes, (size_t)b->H, cudaMemcpyHostToDevice, s));
+        CU(cudaEventRecord(b->ev_copy[half], s));
+    }
+    return PT_OK;
+}
+
+int read_results(pt_batch *b, int32_t *out_ij, int32_t *out_raw, float *out_resp, cudaStream_t s)
+{
+    const size_t n = (size_t)b->n;
+    int rc = b->h_out.ensure(n * 32);
+    if (rc) return rc;
+    int4 *hp = reinterpret_cast<int4 *>(b->h_out.p);
+    float *hr = reinterpret_cast<float *>((char *)b->h_out.p + n * 16);
+    CU(cudaMemcpyAsync(hp, b->d_pos, n * 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hr, b->d_resp, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (size_t v = 0; v < n; ++v) {
+        if (out_ij) { out_ij[2 * v] = hp[v].x; out_ij[2 * v + 1] = hp[v].y; }
+        if (out_raw) { out_raw[2 * v] = hp[v].z; out_raw[2 * v + 1] = hp[v].w; }
+        if (out_resp) out_resp[v] = hr[v];
+    }
+    return PT_OK;
+}
+
+} // namespace
+
+// =============================================================================
+extern "C" {
+
+int pt_version(void) { return PT_VERSION; }
+const char *pt_last_error(void) { return g_err.c_str(); }
+
+int pt_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+double pt_sigma(double tw) { return sigma_of(tw); }
+int pt_kernel_len(double tw) { return tw > 0 ? kernel_len_of(tw) : fail(PT_ERR_ARG, "target_width must be > 0"); }
+int pt_default_window(double tw) { return 4 * (int)std::ceil(sigma_of(tw)) + 1; }
+
+int pt_factors_f32(double tw, int darker, float *row_p, float *row_m, float *col_p, float *col_m)
+{
+    if (!(tw > 0)) return fail(PT_ERR_ARG, "target_width must be > 0");
+    std::vector<float> rp, rm, cp, cm;
+    make_taps(tw, darker != 0, PT_PIX_F32, rp, rm, cp, cm);
+    const size_t l = rp.size();
+    if (row_p) memcpy(row_p, rp.data(), l * 4);
+    if (row_m) memcpy(row_m, rm.data(), l * 4);
+    if (col_p) memcpy(col_p, cp.data(), l * 4);
+    if (col_m) memcpy(col_m, cm.data(), l * 4);
+    return (int)l;
+}
+
+int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, int darker, int pixel,
+                    int device, pt_batch **out)
+{
+    if (!out) return fail(PT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n < 1 || n > 65535) return fail(PT_ERR_ARG, "n must be in 1..65535 (got %d)", n);
+    if (H < 1 || W < 1) return fail(PT_ERR_ARG, "frame size must be positive (got %dx%d)", H, W);
+    if (!(tw > 0) || !std::isfinite(tw)) return fail(PT_ERR_ARG, "target_width must be a positive finite number");
+    if (ws_rows < 1 || ws_cols < 1) return fail(PT_ERR_ARG, "window_size must be >= 1 (got %dx%d)", ws_rows, ws_cols);
+    if (pixel != PT_PIX_U8 && pixel != PT_PIX_F32) return fail(PT_ERR_ARG, "unknown pixel type %d", pixel);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PT_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+
+    const int L = kernel_len_of(tw);
+    const int Lpad = ((L + pt::kTapChunk - 1) / pt::kTapChunk) * pt::kTapChunk;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (pt::generic_smem_bytes(L, Lpad) > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(PT_ERR_UNSUPPORTED, "kernel length %d (target_width %g) needs %zu B shared memory, device allows %zu",
+                    L, tw, pt::generic_smem_bytes(L, Lpad), (size_t)prop.sharedMemPerBlockOptin);
+
+    pt_batch *b = new (std::nothrow) pt_batch();
+    if (!b) return fail(PT_ERR_NOMEM, "out of host memory");
+    b->n = n; b->H = H; b->W = W; b->tw = tw; b->darker = darker != 0; b->pixel = pixel; b->device = device;
+    b->L = L; b->w = L / 2; b->Lpad = Lpad;
+    configure_window(b, ws_rows, ws_cols);
+    b->own_pitch = pixel == PT_PIX_U8 ? (((size_t)W + 15) & ~(size_t)15) : (((size_t)W + 3) & ~(size_t)3);
+    b->own_stride = b->own_pitch * (size_t)H;
+
+    std::vector<float> rp, rm, cp, cm;
+    make_taps(tw, b->darker, pixel, rp, rm, cp, cm);
+    std::vector<float2> trow(Lpad, make_float2(0.f, 0.f)), tcol(Lpad, make_float2(0.f, 0.f));
+    for (int k = 0; k < L; ++k) { trow[k] = make_float2(rp[k], rm[k]); tcol[k] = make_float2(cp[k], cm[k]); }
+
+    int rc = PT_OK;
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == PT_OK) rc = fail(PT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    cu(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int i = 0; i < 2; ++i) {
+        cu(cudaEventCreateWithFlags(&b->ev_copy[i], cudaEventDisableTiming), "cudaEventCreate");
+        cu(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    cu(cudaMalloc(&b->d_taps_row, sizeof(float2) * Lpad), "cudaMalloc taps");
+    cu(cudaMalloc(&b->d_taps_col, sizeof(float2) * Lpad), "cudaMalloc taps");
+    cu(cudaMalloc(&b->d_fill, sizeof(float) * n), "cudaMalloc fill");
+    cu(cudaMalloc(&b->d_fill_i, sizeof(int) * n), "cudaMalloc fill");
+    cu(cudaMalloc(&b->d_guess, sizeof(int2) * n), "cudaMalloc guess");
+    cu(cudaMalloc(&b->d_center, sizeof(int2) * n), "cudaMalloc center");
+    cu(cudaMalloc(&b->d_keys, sizeof(unsigned long long) * n), "cudaMalloc keys");
+    cu(cudaMalloc(&b->d_counters, sizeof(unsigned int) * n), "cudaMalloc counters");
+    cu(cudaMalloc(&b->d_hist, sizeof(unsigned int) * 512 * (size_t)n), "cudaMalloc hist");
+    cu(cudaMalloc(&b->d_pos, sizeof(int4) * n), "cudaMalloc pos");
+    cu(cudaMalloc(&b->d_resp, sizeof(float) * n), "cudaMalloc resp");
+    if (rc == PT_OK) {
+        cu(cudaMemcpy(b->d_taps_row, trow.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
+        cu(cudaMemcpy(b->d_taps_col, tcol.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
+        cu(cudaMemset(b->d_keys, 0, sizeof(unsigned long long) * n), "memset");
+        cu(cudaMemset(b->d_counters, 0, sizeof(unsigned int) * n), "memset");
+        cu(cudaMemset(b->d_hist, 0, sizeof(unsigned int) * 512 * (size_t)n), "memset");
+        cu(cudaMemset(b->d_pos, 0, sizeof(int4) * n), "memset");
+        cu(cudaMemset(b->d_resp, 0, sizeof(float) * n), "memset");
+    }
+    if (rc != PT_OK) { pt_batch_destroy(b); return rc; }
+    b->h_fill.assign(n, 0);
+    b->use45 = true;
+    *out = b;
+    return PT_OK;
+}
+
+void pt_batch_destroy(pt_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    for (auto &ln : b->lanes) {
+        if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
+        ln.h_crops.release(); ln.h_res.release(); ln.d_crops.release();
+    }
+    cudaFree(b->d_taps_row); cudaFree(b->d_taps_col); cudaFree(b->d_fill); cudaFree(b->d_fill_i);
+    cudaFree(b->d_guess); cudaFree(b->d_center); cudaFree(b->d_keys); cudaFree(b->d_counters);
+    cudaFree(b->d_hist); cudaFree(b->d_pos); cudaFree(b->d_resp);
+    for (int i = 0; i < 2; ++i) {
+        b->d_frames[i].release(); b->h_stage[i].release();
+        if (b->ev_copy[i]) cudaEventDestroy(b->ev_copy[i]);
+        if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
+    }
+    b->d_traj_pos.release(); b->d_traj_resp.release(); b->d_map.release(); b->h_out.release();
+    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    delete b;
+}
+
+int pt_batch_set_window(pt_batch *b, int ws_rows, int ws_cols)
+{
+    if (!b) return fail(PT_ERR_ARG, "batch is NULL");
+    if (ws_rows < 1 || ws_cols < 1) return fail(PT_ERR_ARG, "window_size must be >= 1 (got %dx%d)", ws_rows, ws_cols);
+    configure_window(b, ws_rows, ws_cols);
+    return PT_OK;
+}
+
+int pt_batch_set_frames(pt_batch *b, const void *const *frames, size_t pitch)
+{
+    if (!b || !frames) return fail(PT_ERR_ARG, "NULL argument");
+    for (int v = 0; v < b->n; ++v) if (!frames[v]) return fail(PT_ERR_ARG, "frames[%d] is NULL", v);
+    int rc = set_device(b);
+    if (rc) return rc;
+    // make sure no step still reads the slot we are about to overwrite
+    CU(cudaStreamSynchronize(b->stream));
+    rc = upload_frames(b, frames, pitch, b->cur_slot, b->stream);
+    if (rc) return rc;
+    b->have_frames = true;
+    b->bound_base = nullptr;
+    return PT_OK;
+}
+
+int pt_batch_bind_device_frames(pt_batch *b, const void *dev_base, size_t frame_stride, size_t pitch)
+{
+    if (!b || !dev_base) return fail(PT_ERR_ARG, "NULL argument");
+    if (pitch < (size_t)b->W) return fail(PT_ERR_ARG, "pitch %zu smaller than W %d", pitch, b->W);
+    b->bound_base = dev_base; b->bound_stride = frame_stride; b->bound_pitch = pitch;
+    return PT_OK;
+}
+
+int pt_batch_compute_fill(pt_batch *b, int *fills_out)
+{
+    if (!b) return fail(PT_ERR_ARG, "batch is NULL");
+    int rc = set_device(b);
+    if (rc) return rc;
+    const void *base; size_t stride, pitch;
+    rc = current_frames(b, &base, &stride, &pitch);
+    if (rc) return rc;
+    cudaError_t e = pt::launch_mode(base, stride, (int)pitch, b->H, b->W, b->n, b->pixel, b->d_hist,
+                                    b->d_fill, b->d_fill_i, b->stream);
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "mode kernel launch failed: %s", cudaGetErrorString(e));
+    b->launches += 2;
+    CU(cudaMemcpyAsync(b->h_fill.data(), b->d_fill_i, sizeof(int) * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    b->fill_set = true;
+    if (fills_out) memcpy(fills_out, b->h_fill.data(), sizeof(int) * (size_t)b->n);
+    return PT_OK;
+}
+
+int pt_batch_set_fill(pt_batch *b, const int *fills)
+{
+    if (!b || !fills) return fail(PT_ERR_ARG, "NULL argument");
+    int rc = set_device(b);
+    if (rc) return rc;
+    std::vector<float> f(b->n);
+    for (int v = 0; v < b->n; ++v) {
+        if (fills[v] < 0 || fills[v] > 255) return fail(PT_ERR_ARG, "fill[%d]=%d outside 0..255", v, fills[v]);
+        b->h_fill[v] = fills[v];
+        f[v] = b->pixel == PT_PIX_U8 ? (float)fills[v] : (float)fills[v] / 255.0f;
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    CU(cudaMemcpy(b->d_fill, f.data(), sizeof(float) * (size_t)b->n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b->d_fill_i, b->h_fill.data(), sizeof(int) * (size_t)b->n, cudaMemcpyHostToDevice));
+    b->fill_set = true;
+    return PT_OK;
+}
+
+int pt_batch_set_guess(pt_batch *b, const int32_t *guess_ij)
+{
+    if (!b || !guess_ij) return fail(PT_ERR_ARG, "NULL argument");
+    int rc = set_device(b);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(b->stream));
+    return upload_guess(b, guess_ij, b->stream);
+}
+
+int pt_batch_step(pt_batch *b, const int32_t *guess_ij, int32_t *out_ij, int32_t *out_raw_ij, float *out_resp)
+{
+    if (!b) return fail(PT_ERR_ARG, "batch is NULL");
+    int rc = set_device(b);
+    if (rc) return rc;
+    if (!b->fill_set) return fail(PT_ERR_STATE, "fill value not set: call pt_batch_compute_fill or pt_batch_set_fill");
+    const void *base; size_t stride, pitch;
+    rc = current_frames(b, &base, &stride, &pitch);
+    if (rc) return rc;
+    if (guess_ij) { rc = upload_guess(b, guess_ij, b->stream); if (rc) return rc; }
+    else if (!b->guess_set) return fail(PT_ERR_STATE, "no guess on the device: pass guess_ij or call pt_batch_set_guess");
+    pt::WinArgs a = make_args(b, base, stride, pitch, b->H, b->W, b->d_guess, b->n);
+    a.next_guess = b->d_guess;
+    rc = launch_step(b, a, b->n, b->stream);
+    if (rc) return rc;
+    if (out_ij || out_raw_ij || out_resp) return read_results(b, out_ij, out_raw_ij, out_resp, b->stream);
+    return PT_OK;
+}
+
+int pt_batch_track_device_async(pt_batch *b, const void *dev_base, size_t step_stride, size_t frame_stride,
+                                size_t pitch, int T, void *stream)
+{
+    if (!b || !dev_base) return fail(PT_ERR_ARG, "NULL argument");
+    if (T < 1) return fail(PT_ERR_ARG, "T must be >= 1");
+    if (pitch < (size_t)b->W) return fail(PT_ERR_ARG, "pitch %zu smaller than W %d", pitch, b->W);
+    int rc = set_device(b);
+    if (rc) return rc;
+    if (!b->fill_set) return fail(PT_ERR_STATE, "fill value not set");
+    if (!b->guess_set) return fail(PT_ERR_STATE, "no guess on the device: call pt_batch_set_guess");
+    rc = b->d_traj_pos.ensure(sizeof(int4) * (size_t)b->n * T); if (rc) return rc;
+    rc = b->d_traj_resp.ensure(sizeof(float) * (size_t)b->n * T); if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : b->stream;
+    const size_t es = px_size(b->pixel);
+    for (int t = 0; t < T; ++t) {
+        const void *frames = (const char *)dev_base + (size_t)t * step_stride * es;
+        pt::WinArgs a = make_args(b, frames, frame_stride, pitch, b->H, b->W, b->d_guess, b->n);
+        a.next_guess = b->d_guess;
+        a.traj_pos = (int4 *)b->d_traj_pos.p + (size_t)t * b->n;
+        a.traj_resp = (float *)b->d_traj_resp.p + (size_t)t * b->n;
+        rc = launch_step(b, a, b->n, s);
+        if (rc) return rc;
+    }
+    return PT_OK;
+}
+
+int pt_batch_read_track(pt_batch *b, int T, int32_t *out_ij, float *out_resp)
+{
+    if (!b) return fail(PT_ERR_ARG, "batch is NULL");
+    int rc = set_device(b);
+    if (rc) return rc;
+    const size_t cnt = (size_t)b->n * T;
+    if (b->d_traj_pos.cap < cnt * sizeof(int4)) return fail(PT_ERR_STATE, "no trajectory of %d steps on the device", T);
+    rc = b->h_out.ensure(std::max<size_t>(cnt * 20, (size_t)b->n * 32));
+    if (rc) return rc;
+    int4 *hp = (int4 *)b->h_out.p;
+    float *hr = (float *)((char *)b->h_out.p + cnt * 16);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(hp, b->d_traj_pos.p, cnt * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hr, b->d_traj_resp.p, cnt * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < cnt; ++i) {
+        if (out_ij) { out_ij[2 * i] = hp[i].x; out_ij[2 * i + 1] = hp[i].y; }
+        if (out_resp) out_resp[i] = hr[i];
+    }
+    return PT_OK;
+}
+
+int pt_batch_track_device(pt_batch *b, const void *dev_base, size_t step_stride, size_t frame_stride,
+                          size_t pitch, int T, int32_t *out_ij, float *out_resp)
+{
+    int rc = pt_batch_track_device_async(b, dev_base, step_stride, frame_stride, pitch, T, nullptr);
+    if (rc) return rc;
+    return pt_batch_read_track(b, T, out_ij, out_resp);
+}
+
+} // extern "C"
+
+// ---- host-resident frames ----------------------------------------------------
+namespace {
+
+// Gather the footprint of one window from a host frame into a crop of pitch
+// `cp` elements: everything outside the frame is the fill value, exactly the
+// PaddedView the reference filters (src/PawsomeTracker.jl:48).
+template <typename T>
+void gather_crop(const T *frame, size_t pitch, int H, int W, T fillv, int oy, int ox, int fr, int fc,
+                 size_t cp, T *dst)
+{
+    const int xa = std::max(0, -ox), xb = std::min(fc, W - ox); // crop cols [xa, xb) are inside the frame
+    for (int y = 0; y < fr; ++y) {
+        T *d = dst + (size_t)y * cp;
+        const int Y = oy + y;
+        if (Y < 0 || Y >= H || xa >= xb) { std::fill(d, d + fc, fillv); continue; }
+        if (xa > 0) std::fill(d, d + xa, fillv);
+        memcpy(d + xa, frame + (size_t)Y * pitch + (ox + xa), sizeof(T) * (size_t)(xb - xa));
+        if (xb < fc) std::fill(d + xb, d + fc, fillv);
+    }
+}
+
+struct HostTrack {
+    pt_batch *b;
+    const void *const *frames;
+    int T;
+    size_t pitch;
+    int32_t *out_ij;
+    float *out_resp;
+    std::vector<int32_t> guess; // n×2, host copy of the chain state
+    std::atomic<int> err{PT_OK};
+    std::string err_msg;
+};
+
+// One lane = one host thread + one stream: gather → H2D → kernel → D2H → sync,
+// chained over T steps for its slice of videos.  Lanes never synchronise with
+// one another (videos are independent units — SURVEY §8e).
+void lane_worker(HostTrack *ht, pt_lane *ln)
+{
+    pt_batch *b = ht->b;
+    if (cudaSetDevice(b->device) != cudaSuccess) { ht->err = PT_ERR_CUDA; return; }
+    const int nl = ln->v1 - ln->v0;
+    const int fr = b->wr + 2 * b->w, fc = b->wc + 2 * b->w;
+    const size_t es = px_size(b->pixel);
+    const size_t cp = b->pixel == PT_PIX_U8 ? (((size_t)fc + 15) & ~(size_t)15) : (((size_t)fc + 3) & ~(size_t)3);
+    const size_t crop_elems = cp * (size_t)fr;
+    int4 *hres = (int4 *)ln->h_res.p;
+    float *hresp = (float *)((char *)ln->h_res.p + (size_t)nl * 16);
+    std::vector<int> oy(nl), ox(nl);
+
+    for (int t = 0; t < ht->T && ht->err.load() == PT_OK; ++t) {
+        for (int i = 0; i < nl; ++i) {
+            const int v = ln->v0 + i;
+            const int gi = ht->guess[2 * v], gj = ht->guess[2 * v + 1];
+            oy[i] = gi - 1 - b->rr - b->w; ox[i] = gj - 1 - b->rc - b->w;
+            const void *f = ht->frames[(size_t)t * b->n + v];
+            if (b->pixel == PT_PIX_U8)
+                gather_crop<uint8_t>((const uint8_t *)f, ht->pitch, b->H, b->W, (uint8_t)b->h_fill[v], oy[i], ox[i],
+                                     fr, fc, cp, (uint8_t *)ln->h_crops.p + crop_elems * i);
+            else
+                gather_crop<float>((const float *)f, ht->pitch, b->H, b->W, (float)b->h_fill[v] / 255.0f, oy[i], ox[i],
+                                   fr, fc, cp, (float *)ln->h_crops.p + crop_elems * i);
+        }
+        cudaError_t e = cudaMemcpyAsync(ln->d_crops.p, ln->h_crops.p, crop_elems * es * nl, cudaMemcpyHostToDevice, ln->stream);
+        if (e == cudaSuccess) {
+            pt::WinArgs a = make_args(b, ln->d_crops.p, crop_elems, cp, fr, fc, b->d_center + ln->v0, nl);
+            a.fill = b->d_fill + ln->v0;
+            a.keys = b->d_keys + ln->v0; a.counters = b->d_counters + ln->v0;
+            a.out_pos = b->d_pos + ln->v0; a.out_resp = b->d_resp + ln->v0;
+            cudaError_t le;
+            if (b->use45 && pt::window45_supported(a)) le = pt::launch_window45(a, nl, b->pixel, ln->stream);
+            else { decompose(a, nl); le = pt::launch_generic(a, nl, b->pixel, ln->stream); }
+            e = le;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hres, b->d_pos + ln->v0, sizeof(int4) * nl, cudaMemcpyDeviceToHost, ln->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hresp, b->d_resp + ln->v0, sizeof(float) * nl, cudaMemcpyDeviceToHost, ln->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ln->stream);
+        if (e != cudaSuccess) {
+            int expected = PT_OK;
+            if (ht->err.compare_exchange_strong(expected, PT_ERR_CUDA)) ht->err_msg = cudaGetErrorString(e);
+            return;
+        }
+        for (int i = 0; i < nl; ++i) {
+            const int v = ln->v0 + i;
+            // crop row/col 1-based → frame 1-based, then clamp (src/PawsomeTracker.jl:60-61)
+            const int raw_i = oy[i] + hres[i].z, raw_j = ox[i] + hres[i].w;
+            const int ci = std::min(std::max(raw_i, 1), b->H), cj = std::min(std::max(raw_j, 1), b->W);
+            ht->guess[2 * v] = ci; ht->guess[2 * v + 1] = cj;
+            int32_t *o = ht->out_ij + ((size_t)t * b->n + v) * 2;
+            o[0] = ci; o[1] = cj;
+            if (ht->out_resp) ht->out_resp[(size_t)t * b->n + v] = hresp[i];
+        }
+    }
+}
+
+int ensure_lanes(pt_batch *b)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    int want = (int)std::min<unsigned>(std::min<unsigned>(hw, 16u), (unsigned)b->n);
+    if (const char *env = getenv("PT_HOST_LANES")) { int k = atoi(env); if (k >= 1) want = std::min(k, b->n); }
+    if ((int)b->lanes.size() != want) {
+        for (auto &ln : b->lanes) { if (ln.stream) cudaStreamDestroy(ln.stream); ln.h_crops.release(); ln.h_res.release(); ln.d_crops.release(); }
+        b->lanes.assign(want, pt_lane());
+        for (int i = 0; i < want; ++i) {
+            b->lanes[i].v0 = (int)((long long)b->n * i / want);
+            b->lanes[i].v1 = (int)((long long)b->n * (i + 1) / want);
+            CU(cudaStreamCreateWithFlags(&b->lanes[i].stream, cudaStreamNonBlocking));
+        }
+    }
+    const int fr = b->wr + 2 * b->w, fc = b->wc + 2 * b->w;
+    const size_t es = px_size(b->pixel);
+    const size_t cp = b->pixel == PT_PIX_U8 ? (((size_t)fc + 15) & ~(size_t)15) : (((size_t)fc + 3) & ~(size_t)3);
+    for (auto &ln : b->lanes) {
+        const size_t nl = (size_t)(ln.v1 - ln.v0);
+        int rc = ln.h_crops.ensure(cp * fr * es * nl); if (rc) return rc;
+        rc = ln.d_crops.ensure(cp * fr * es * nl); if (rc) return rc;
+        rc = ln.h_res.ensure(nl * 20); if (rc) return rc;
+    }
+    std::vector<int2> c(b->n, make_int2(b->rr + b->w + 1, b->rc + b->w + 1));
+    CU(cudaMemcpy(b->d_center, c.data(), sizeof(int2) * (size_t)b->n, cudaMemcpyHostToDevice));
+    return PT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pitch, int mode,
+                        int32_t *out_ij, float *out_resp)
+{
+    if (!b || !frames || !out_ij) return fail(PT_ERR_ARG, "NULL argument");
+    if (T < 1) return fail(PT_ERR_ARG, "T must be >= 1");
+    if (pitch < (size_t)b->W) return fail(PT_ERR_ARG, "pitch %zu smaller than W %d", pitch, b->W);
+    if (mode != 0 && mode != 1) return fail(PT_ERR_ARG, "mode must be 0 (footprint) or 1 (whole frames)");
+    int rc = set_device(b);
+    if (rc) return rc;
+    if (!b->fill_set) return fail(PT_ERR_STATE, "fill value not set");
+    if (!b->guess_set) return fail(PT_ERR_STATE, "no guess on the device: call pt_batch_set_guess");
+    const size_t n = (size_t)b->n;
+
+    if (mode == 1) {
+        // whole frames: upload step t+1 on the copy stream into the other slot
+        // while step t's kernel runs; one D2H of the result per step.
+        b->bound_base = nullptr;
+        CU(cudaStreamSynchronize(b->stream));
+        rc = upload_frames(b, frames, pitch, 0, b->copy_stream); if (rc) return rc;
+        CU(cudaEventRecord(b->ev_done[0], b->copy_stream));
+        for (int t = 0; t < T; ++t) {
+            const int slot = t & 1;
+            if (t + 1 < T) {
+                // slot^1 was last read by step t-1, which we synchronised on below
+                rc = upload_frames(b, frames + (size_t)(t + 1) * n, pitch, slot ^ 1, b->copy_stream); if (rc) return rc;
+                CU(cudaEventRecord(b->ev_done[slot ^ 1], b->copy_stream));
+            }
+            CU(cudaStreamWaitEvent(b->stream, b->ev_done[slot], 0));
+            pt::WinArgs a = make_args(b, b->d_frames[slot].p, b->own_stride, b->own_pitch, b->H, b->W, b->d_guess, b->n);
+            a.next_guess = b->d_guess;
+            rc = launch_step(b, a, b->n, b->stream); if (rc) return rc;
+            rc = read_results(b, out_ij + (size_t)t * n * 2, nullptr, out_resp ? out_resp + (size_t)t * n : nullptr, b->stream);
+            if (rc) return rc;
+        }
+        b->cur_slot = (T - 1) & 1;
+        b->have_frames = true;
+        return PT_OK;
+    }
+
+    // footprint streaming
+    rc = ensure_lanes(b); if (rc) return rc;
+    HostTrack ht;
+    ht.b = b; ht.frames = frames; ht.T = T; ht.pitch = pitch; ht.out_ij = out_ij; ht.out_resp = out_resp;
+    ht.guess.resize(n * 2);
+    CU(cudaStreamSynchronize(b->stream));
+    CU(cudaMemcpy(ht.guess.data(), b->d_guess, sizeof(int2) * n, cudaMemcpyDeviceToHost));
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < b->lanes.size(); ++i) th.emplace_back(lane_worker, &ht, &b->lanes[i]);
+    lane_worker(&ht, &b->lanes[0]);
+    for (auto &t : th) t.join();
+    b->launches += (long long)T * (long long)b->lanes.size();
+    if (ht.err.load() != PT_OK) return fail(ht.err.load(), "footprint streaming failed: %s", ht.err_msg.c_str());
+    // leave the chain state on the device, as pt_batch_step would
+    CU(cudaMemcpy(b->d_guess, ht.guess.data(), sizeof(int2) * n, cudaMemcpyHostToDevice));
+    return PT_OK;
+}
+
+int pt_batch_response_map(pt_batch *b, int v, int gi, int gj, float *out_map)
+{
+    if (!b || !out_map) return fail(PT_ERR_ARG, "NULL argument");
+    if (v < 0 || v >= b->n) return fail(PT_ERR_ARG, "video index %d out of range", v);
+    int rc = set_device(b);
+    if (rc) return rc;
+    if (!b->fill_set) return fail(PT_ERR_STATE, "fill value not set");
+    const void *base; size_t stride, pitch;
+    rc = current_frames(b, &base, &stride, &pitch); if (rc) return rc;
+    const size_t cnt = (size_t)b->wr * b->wc;
+    rc = b->d_map.ensure(cnt * 4); if (rc) return rc;
+    const size_t es = px_size(b->pixel);
+    pt::WinArgs a = make_args(b, (const char *)base + (size_t)v * stride * es, stride, pitch, b->H, b->W, nullptr, 1);
+    a.rect_mode = 1; a.ry0 = gi - 1 - b->rr; a.rx0 = gj - 1 - b->rc;
+    a.fill = b->d_fill + v; a.keys = b->d_keys + v; a.counters = b->d_counters + v;
+    a.out_pos = b->d_pos + v; a.out_resp = b->d_resp + v;
+    a.map_out = (float *)b->d_map.p;
+    rc = launch_step(b, a, 1, b->stream); if (rc) return rc;
+    CU(cudaMemcpyAsync(out_map, b->d_map.p, cnt * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return PT_OK;
+}
+
+int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int wc,
+                         int *oi, int *oj, int *raw_i, int *raw_j, float *resp)
+{
+    if (!b) return fail(PT_ERR_ARG, "batch is NULL");
+    if (v < 0 || v >= b->n) return fail(PT_ERR_ARG, "video index %d out of range", v);
+    if (wr < 1 || wc < 1) return fail(PT_ERR_ARG, "rectangle must be non-empty");
+    if ((long long)wr * wc > 0x7FFFFFFFll) return fail(PT_ERR_ARG, "rectangle too large");
+    int rc = set_device(b);
+    if (rc) return rc;
+    if (!b->fill_set) return fail(PT_ERR_STATE, "fill value not set");
+    const void *base; size_t stride, pitch;
+    rc = current_frames(b, &base, &stride, &pitch); if (rc) return rc;
+    const size_t es = px_size(b->pixel);
+    pt::WinArgs a = make_args(b, (const char *)base + (size_t)v * stride * es, stride, pitch, b->H, b->W, nullptr, 1);
+    a.rect_mode = 1; a.ry0 = y0; a.rx0 = x0; a.wr = wr; a.wc = wc;
+    a.fill = b->d_fill + v; a.keys = b->d_keys + v; a.counters = b->d_counters + v;
+    a.out_pos = b->d_pos + v; a.out_resp = b->d_resp + v;
+    rc = launch_step(b, a, 1, b->stream); if (rc) return rc;
+    int4 p; float r;
+    CU(cudaMemcpyAsync(&p, b->d_pos + v, sizeof p, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(&r, b->d_resp + v, sizeof r, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    if (oi) *oi = p.x; if (oj) *oj = p.y; if (raw_i) *raw_i = p.z; if (raw_j) *raw_j = p.w; if (resp) *resp = r;
+    return PT_OK;
+}
+
+long long pt_batch_launch_count(const pt_batch *b) { return b ? b->launches : 0; }
+
+const char *pt_batch_kernel_name(const pt_batch *b)
+{
+    if (!b) return "";
+    pt::WinArgs a;
+    memset(&a, 0, sizeof a);
+    a.wr = b->wr; a.wc = b->wc; a.L = b->L; a.w = b->w;
+    if (b->use45 && pt::window45_supported(a)) return pt::window45_name();
+    return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
+}
+
+void *pt_batch_stream(const pt_batch *b) { return b ? (void *)b->stream : nullptr; }
+
+// ---- single tracker ----------------------------------------------------------
+int pt_tracker_create(int H, int W, double tw, int ws_rows, int ws_cols, int darker, int pixel, int device,
+                      pt_tracker **out)
+{
+    if (!out) return fail(PT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    pt_batch *b = nullptr;
+    int rc = pt_batch_create(1, H, W, tw, ws_rows, ws_cols, darker, pixel, device, &b);
+    if (rc) return rc;
+    pt_tracker *t = new (std::nothrow) pt_tracker();
+    if (!t) { pt_batch_destroy(b); return fail(PT_ERR_NOMEM, "out of host memory"); }
+    t->b = b;
+    *out = t;
+    return PT_OK;
+}
+
+void pt_tracker_destroy(pt_tracker *t)
+{
+    if (!t) return;
+    pt_batch_destroy(t->b);
+    delete t;
+}
+
+pt_batch *pt_tracker_batch(pt_tracker *t) { return t ? t->b : nullptr; }
+
+int pt_tracker_set_frame(pt_tracker *t, const void *frame, size_t pitch)
+{
+    if (!t) return fail(PT_ERR_ARG, "tracker is NULL");
+    const void *f[1] = {frame};
+    return pt_batch_set_frames(t->b, f, pitch);
+}
+
+int pt_tracker_compute_fill(pt_tracker *t, int *fill_out)
+{
+    if (!t) return fail(PT_ERR_ARG, "tracker is NULL");
+    return pt_batch_compute_fill(t->b, fill_out);
+}
+
+int pt_tracker_set_fill(pt_tracker *t, int fill)
+{
+    if (!t) return fail(PT_ERR_ARG, "tracker is NULL");
+    return pt_batch_set_fill(t->b, &fill);
+}
+
+int pt_tracker_step(pt_tracker *t, int gi, int gj, int *oi, int *oj, float *resp)
+{
+    if (!t) return fail(PT_ERR_ARG, "tracker is NULL");
+    int32_t g[2] = {gi, gj}, o[2] = {0, 0};
+    float r = 0.f;
+    int rc = pt_batch_step(t->b, g, o, nullptr, &r);
+    if (rc) return rc;
+    if (oi) *oi = o[0]; if (oj) *oj = o[1]; if (resp) *resp = r;
+    return PT_OK;
+}
+
+int pt_tracker_step_host(pt_tracker *t, const void *frame, size_t pitch, int gi, int gj, int *oi, int *oj, float *resp)
+{
+    if (!t || !frame) return fail(PT_ERR_ARG, "NULL argument");
+    int32_t g[2] = {gi, gj}, o[2] = {0, 0};
+    float r = 0.f;
+    int rc = pt_batch_set_guess(t->b, g);
+    if (rc) return rc;
+    const void *f[1] = {frame};
+    rc = pt_batch_track_host(t->b, f, 1, pitch, 0, o, &r);
+    if (rc) return rc;
+    if (oi) *oi = o[0]; if (oj) *oj = o[1]; if (resp) *resp = r;
+    return PT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,335 @@
+// pt_kernels.cu — generic DoG-window + argmax kernel (any window size, any
+// kernel length that fits shared memory) and the mode (fill value) kernels.
+//
+// What it replaces: imfilter!(…, buff, img, kernel, NoPad(), window_indices)
+// followed by findmax over the window view — src/PawsomeTracker.jl:57-59 — for
+// every window of a batch in one launch.  Nothing here is derived from the
+// reference's code (which is a dense l×l Float64 loop inside ImageFiltering.jl);
+// the design is a streaming separable filter:
+//
+//   grid = (column strips of 32 outputs, row chunks, windows)
+//   each CTA marches down its strip in batches of 32 footprint rows:
+//     stage    32 × (32+2w) pixels → smem as (pixel − fill)   [0 outside the frame]
+//     row pass both Gaussians at once → ring buffer of l+31 rows (float2 per output)
+//     col pass 32 output rows whose 2w+1 ring rows are complete, fused with the
+//              subtraction, the darker_target sign and a running per-thread argmax
+//   block argmax → 64-bit atomicMax per window; the last CTA of a window decodes
+//   the key, clamps and publishes (position, response, next guess).
+//
+// The row pass is computed exactly once per footprint row of the chunk and the
+// column pass once per output, i.e. the algorithmic FLOP count of SURVEY §8(d)
+// when chunks == 1.  Each thread register-tiles 8 outputs along the filter
+// direction so one shared-memory load feeds 16 FMAs.
+#include "pt_kernels.cuh"
+
+namespace pt {
+
+template <typename PixT> __device__ __forceinline__ float px_value(const PixT *p);
+template <> __device__ __forceinline__ float px_value<uint8_t>(const uint8_t *p) { return (float)__ldg(p); }
+template <> __device__ __forceinline__ float px_value<float>(const float *p) { return __ldg(p); }
+
+__device__ __forceinline__ bool key_better(float v, unsigned int idx, float bv, unsigned int bidx)
+{
+    return v > bv || (v == bv && idx < bidx);
+}
+
+template <typename PixT>
+__global__ void __launch_bounds__(kGenericThreads)
+dog_rect_argmax_generic(const WinArgs a)
+{
+    constexpr int TW = kTileCols, TB = kBatchRows, R = 8, C = kTapChunk;
+    static_assert(TW == 32 && TB == 32, "lane/warp mapping assumes 32x32 tiles");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = a.L, w = a.w, Lpad = a.Lpad;
+    const int PIN = (TW + Lpad - 1) | 1;   // odd pitch: lanes walk rows conflict-free
+    const int RING = L + TB - 1;
+    float2 *s_trow = reinterpret_cast<float2 *>(smem_raw);
+    float2 *s_tcol = s_trow + Lpad;
+    constexpr int RP = TW + 1;                            // ring row pitch (float2): odd → row-pass stores conflict-free
+    float2 *s_ring = s_tcol + Lpad;                       // [RING][RP]
+    float *s_in = reinterpret_cast<float *>(s_ring + (size_t)RING * RP); // [TB][PIN]
+    __shared__ unsigned long long s_best[kGenericThreads / 32];
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v = blockIdx.z, strip = blockIdx.x, chunk = blockIdx.y;
+
+    int wy0, wx0;
+    if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
+    else { int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
+
+    const int c0 = strip * TW;
+    const int r0 = chunk * a.CH;
+    const int ch = min(a.CH, a.wr - r0);   // output rows of this chunk
+    const int sw = min(TW, a.wc - c0);     // output cols of this strip
+    const int nfoot = ch + 2 * w;          // footprint rows of this chunk
+    const int nb = (nfoot + TB - 1) / TB;
+
+    for (int k = tid; k < Lpad; k += kGenericThreads) { s_trow[k] = a.taps_row[k]; s_tcol[k] = a.taps_col[k]; }
+    for (int e = tid; e < RING * RP; e += kGenericThreads) s_ring[e] = make_float2(0.f, 0.f);
+
+    const float fill = a.fill[v];
+    const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
+    const int valid_cols = TW + 2 * w;     // tile columns that carry real footprint
+
+    float best_v = -INFINITY;
+    unsigned int best_i = 0xFFFFFFFFu;
+
+    for (int b = 0; b < nb; ++b) {
+        // ---- stage TB footprint rows (warp per row, lanes along the row: coalesced)
+        for (int rrow = warp; rrow < TB; rrow += kGenericThreads / 32) {
+            const int f = b * TB + rrow;
+            const int Y = wy0 + r0 - w + f;
+            const bool yok = (Y >= 0) && (Y < a.H) && (f < nfoot);
+            const PixT *rowp = frame + (size_t)(yok ? Y : 0) * a.pitch;
+            float *dst = s_in + rrow * PIN;
+            const int X0 = wx0 + c0 - w;
+            for (int t = lane; t < PIN; t += 32) {
+                const int X = X0 + t;
+                float val = 0.f;
+                if (yok && X >= 0 && X < a.W && t < valid_cols) val = px_value<PixT>(rowp + X) - fill;
+                dst[t] = val;
+            }
+        }
+        __syncthreads();
+
+        // ---- row pass: lane = footprint row of the batch, warp = group of 8 output columns
+        {
+            const float *src = s_in + lane * PIN + warp * R;
+            float ap[R], am[R], win[R + C - 1];
+#pragma unroll
+            for (int j = 0; j < R; ++j) { ap[j] = 0.f; am[j] = 0.f; }
+#pragma unroll
+            for (int j = 0; j < R - 1; ++j) win[j] = src[j];
+#pragma unroll 1
+            for (int k0 = 0; k0 < Lpad; k0 += C) {
+#pragma unroll
+                for (int t = 0; t < C; ++t) win[R - 1 + t] = src[k0 + R - 1 + t];
+#pragma unroll
+                for (int t = 0; t < C; ++t) {
+                    const float2 g = s_trow[k0 + t];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        ap[j] = fmaf(win[j + t], g.x, ap[j]);
+                        am[j] = fmaf(win[j + t], g.y, am[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < R - 1; ++j) win[j] = win[j + C];
+            }
+            const int f = b * TB + lane;
+            float2 *dst = s_ring + (size_t)(f % RING) * RP + warp * R;
+#pragma unroll
+            for (int j = 0; j < R; ++j) dst[j] = make_float2(ap[j], am[j]);
+        }
+        __syncthreads();
+
+        // ---- column pass: lane = output column, warp = group of 8 output rows
+        const int o_base = b * TB - 2 * w;   // first output row whose support is now complete
+        if (o_base + TB > 0 && o_base < ch) {
+            const int f_start = o_base + warp * R;
+            int slot = f_start % RING;
+            if (slot < 0) slot += RING;
+            const float2 *ring_x = s_ring + lane;
+            float acc[R], wp[R + C - 1], wm[R + C - 1];
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < R - 1; ++j) {
+                const float2 m = ring_x[(size_t)slot * RP];
+                wp[j] = m.x; wm[j] = m.y;
+                slot = (slot + 1 == RING) ? 0 : slot + 1;
+            }
+#pragma unroll 1
+            for (int k0 = 0; k0 < Lpad; k0 += C) {
+#pragma unroll
+                for (int t = 0; t < C; ++t) {
+                    const float2 m = ring_x[(size_t)slot * RP];
+                    wp[R - 1 + t] = m.x; wm[R - 1 + t] = m.y;
+                    slot = (slot + 1 == RING) ? 0 : slot + 1;
+                }
+#pragma unroll
+                for (int t = 0; t < C; ++t) {
+                    const float2 g = s_tcol[k0 + t];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        acc[j] = fmaf(wp[j + t], g.x, acc[j]);
+                        acc[j] = fmaf(wm[j + t], g.y, acc[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < R - 1; ++j) { wp[j] = wp[j + C]; wm[j] = wm[j + C]; }
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int o = f_start + j;
+                if (o >= 0 && o < ch && lane < sw) {
+                    const float val = acc[j] + 0.0f;
+                    const unsigned int idx = (unsigned int)(c0 + lane) * (unsigned int)a.wr + (unsigned int)(r0 + o);
+                    if (key_better(val, idx, best_v, best_i)) { best_v = val; best_i = idx; }
+                    if (a.map_out)
+                        a.map_out[(size_t)v * a.wr * a.wc + (size_t)(r0 + o) * a.wc + (c0 + lane)] = val;
+                }
+            }
+        }
+        // the next batch's staging only touches s_in; its row pass (which
+        // overwrites the oldest ring rows read above) runs after the next barrier
+    }
+
+    // ---- block argmax → one 64-bit atomicMax per CTA
+    unsigned long long key = (best_i == 0xFFFFFFFFu) ? 0ull : pack_key(best_v, best_i);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+        key = o > key ? o : key;
+    }
+    if (lane == 0) s_best[warp] = key;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long k = s_best[0];
+        for (int i = 1; i < kGenericThreads / 32; ++i) k = s_best[i] > k ? s_best[i] : k;
+        atomicMax(a.keys + v, k);
+        __threadfence();
+        const unsigned int total = (unsigned int)(a.strips * a.chunks);
+        const unsigned int prev = atomicAdd(a.counters + v, 1u);
+        s_last = (prev == total - 1u);
+        if (s_last) {
+            __threadfence();
+            const unsigned long long win = atomicExch(a.keys + v, 0ull);
+            a.counters[v] = 0u;
+            publish_result(a, v, win, wy0, wx0);
+        }
+    }
+}
+
+size_t generic_smem_bytes(int L, int Lpad)
+{
+    const int PIN = (kTileCols + Lpad - 1) | 1;
+    const int RING = L + kBatchRows - 1;
+    return (size_t)2 * Lpad * sizeof(float2) + (size_t)RING * (kTileCols + 1) * sizeof(float2) +
+           (size_t)kBatchRows * PIN * sizeof(float);
+}
+
+cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s)
+{
+    const size_t smem = generic_smem_bytes(a.L, a.Lpad);
+    dim3 grid((unsigned)a.strips, (unsigned)a.chunks, (unsigned)n);
+    cudaError_t e;
+    if (pixel == 0) {
+        e = cudaFuncSetAttribute(dog_rect_argmax_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        dog_rect_argmax_generic<uint8_t><<<grid, kGenericThreads, smem, s>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(dog_rect_argmax_generic<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        dog_rect_argmax_generic<float><<<grid, kGenericThreads, smem, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// mode(frame): 256-bin histogram + position of each value's last occurrence in
+// column-major order.  StatsBase.mode returns the value whose count first
+// reaches the final maximum while scanning; a value reaches its final count at
+// its LAST occurrence, so among the values tied for the maximum count the one
+// whose last occurrence comes earliest wins.  (src/PawsomeTracker.jl:47)
+// ---------------------------------------------------------------------------
+constexpr int kModeSplit = 16;   // CTAs per frame
+constexpr int kModeThreads = 256;
+
+template <typename PixT> __device__ __forceinline__ int px_bin(const PixT *p);
+template <> __device__ __forceinline__ int px_bin<uint8_t>(const uint8_t *p) { return (int)__ldg(p); }
+template <> __device__ __forceinline__ int px_bin<float>(const float *p)
+{
+    int b = __float2int_rn(__ldg(p) * 255.0f);
+    return min(max(b, 0), 255);
+}
+
+template <typename PixT>
+__global__ void __launch_bounds__(kModeThreads)
+mode_hist_kernel(const void *frames, size_t frame_stride, int pitch, int H, int W, unsigned int *hist)
+{
+    __shared__ unsigned int s_cnt[256];
+    __shared__ unsigned int s_last[256];
+    const int v = blockIdx.y;
+    const PixT *frame = reinterpret_cast<const PixT *>(frames) + (size_t)v * frame_stride;
+    for (int i = threadIdx.x; i < 256; i += kModeThreads) { s_cnt[i] = 0u; s_last[i] = 0u; }
+    __syncthreads();
+    const int rows_per = (H + gridDim.x - 1) / gridDim.x;
+    const int y0 = blockIdx.x * rows_per, y1 = min(H, y0 + rows_per);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int y = y0 + warp; y < y1; y += kModeThreads / 32) {
+        const PixT *row = frame + (size_t)y * pitch;
+        for (int x0 = 0; x0 < W; x0 += 32) {
+            const int x = x0 + lane;
+            const bool ok = x < W;
+            const int bin = ok ? px_bin<PixT>(row + x) : -1;
+            const unsigned int pos = (unsigned int)x * (unsigned int)H + (unsigned int)y + 1u; // column-major, 1-based
+            // warp-aggregate: one shared-memory atomic per distinct value in the warp
+            unsigned int remaining = __ballot_sync(0xFFFFFFFFu, ok);
+            while (remaining) {
+                const int leader = __ffs(remaining) - 1;
+                const int lbin = __shfl_sync(0xFFFFFFFFu, bin, leader);
+                const bool mine = (bin == lbin);
+                const unsigned int same = __ballot_sync(0xFFFFFFFFu, mine);
+                const unsigned int mx = __reduce_max_sync(0xFFFFFFFFu, mine ? pos : 0u);
+                if (lane == leader) {
+                    atomicAdd(&s_cnt[lbin], (unsigned int)__popc(same));
+                    atomicMax(&s_last[lbin], mx);
+                }
+                remaining &= ~same;
+            }
+        }
+    }
+    __syncthreads();
+    unsigned int *h = hist + (size_t)v * 512;
+    for (int i = threadIdx.x; i < 256; i += kModeThreads) {
+        if (s_cnt[i]) { atomicAdd(h + i, s_cnt[i]); atomicMax(h + 256 + i, s_last[i]); }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mode_pick_kernel(unsigned int *hist, int pixel, float *fill_out, int *fill_int_out)
+{
+    __shared__ unsigned long long s_key[8];
+    const int v = blockIdx.x, i = threadIdx.x;
+    unsigned int *h = hist + (size_t)v * 512;
+    const unsigned int cnt = h[i], last = h[256 + i];
+    // larger count wins; ties → smaller last position
+    unsigned long long key = ((unsigned long long)cnt << 40) | ((unsigned long long)(0xFFFFFFFFu - last) << 8) | (unsigned long long)i;
+    if (cnt == 0) key = 0ull;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+        key = o > key ? o : key;
+    }
+    if ((i & 31) == 0) s_key[i >> 5] = key;
+    __syncthreads();
+    if (i == 0) {
+        unsigned long long k = s_key[0];
+        for (int t = 1; t < 8; ++t) k = s_key[t] > k ? s_key[t] : k;
+        const int bin = (int)(k & 0xFFull);
+        fill_int_out[v] = bin;
+        fill_out[v] = pixel == 0 ? (float)bin : (float)bin / 255.0f;
+    }
+    __syncthreads();
+    h[i] = 0u; h[256 + i] = 0u; // leave the scratch zeroed for the next call
+}
+
+cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int H, int W, int n,
+                        int pixel, unsigned int *hist, float *fill_out, int *fill_int_out,
+                        cudaStream_t s)
+{
+    dim3 grid(kModeSplit, (unsigned)n);
+    if (pixel == 0)
+        mode_hist_kernel<uint8_t><<<grid, kModeThreads, 0, s>>>(frames, frame_stride, pitch, H, W, hist);
+    else
+        mode_hist_kernel<float><<<grid, kModeThreads, 0, s>>>(frames, frame_stride, pitch, H, W, hist);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    mode_pick_kernel<<<n, 256, 0, s>>>(hist, pixel, fill_out, fill_int_out);
+    return cudaGetLastError();
+}
+
+} // namespace pt

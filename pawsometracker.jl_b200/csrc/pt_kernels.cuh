@@ -1,0 +1,94 @@
+// pt_kernels.cuh — device-side argument block and launch prototypes shared by
+// the kernels (pt_kernels.cu, pt_window45.cu) and the C-ABI host layer (pt_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pt {
+
+constexpr int kTileCols = 32;    // output columns per CTA strip (generic kernel)
+constexpr int kBatchRows = 32;   // footprint rows staged per batch (generic kernel)
+constexpr int kTapChunk = 5;     // taps per unrolled chunk; l = 4⌈σ√2⌉+1 ≡ 1 (mod 4), 65 and 245 divide by 5
+constexpr int kGenericThreads = 128;
+
+// One launch = one (trckr::Tracker)(guess) evaluation for every window of the
+// batch (reference: src/PawsomeTracker.jl:55-62).
+struct WinArgs {
+    const void *frames;        // frame of window 0 for this step (u8 or f32)
+    size_t frame_stride;       // elements between consecutive windows' frames
+    int pitch;                 // elements between rows
+    int H, W;                  // frame size
+    const float *fill;         // [n] border fill in pixel units (u8 scale or [0,1])
+    const int2 *guess;         // [n] 1-based (row, col) = (x, y) fields; unused in rect mode
+    int rect_mode;             // 1: window origin is (ry0, rx0) for every window
+    int ry0, rx0;              // 0-based origin of the output rectangle (rect mode)
+    int rr, rc;                // radii = window_size .÷ 2          (:44)
+    int wr, wc;                // output rows / cols of the window  (:56)
+    int L, w, Lpad;            // kernel length, half width, length padded to kTapChunk
+    const float2 *taps_row;    // [Lpad] (narrow, wide) row-pass taps (pixel scale folded in)
+    const float2 *taps_col;    // [Lpad] (narrow, wide) column-pass taps (sign folded in)
+    int strips, chunks, CH;    // CTA decomposition of one window
+    unsigned long long *keys;  // [n] packed running argmax (zero between launches)
+    unsigned int *counters;    // [n] CTA completion counters (zero between launches)
+    int4 *out_pos;             // [n] (i, j clamped; raw_i, raw_j), 1-based
+    float *out_resp;           // [n] maximum response
+    int2 *next_guess;          // [n] clamped result for the next chained step (may alias guess)
+    int4 *traj_pos;            // optional [n] trajectory slot of this step
+    float *traj_resp;          // optional [n]
+    float *map_out;            // optional response maps, [n][wr*wc] row-major (parity instrumentation)
+};
+
+// Orderable packing of (response, column-major index): max key = largest
+// response, ties → smallest column-major index = findmax's "first maximum"
+// (src/PawsomeTracker.jl:59).
+__device__ __forceinline__ unsigned long long pack_key(float v, unsigned int idx)
+{
+    v += 0.0f; // canonicalise -0.0
+    unsigned int b = __float_as_uint(v);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float key_value(unsigned long long k)
+{
+    unsigned int b = (unsigned int)(k >> 32);
+    b = (b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ unsigned int key_index(unsigned long long k)
+{
+    return 0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull);
+}
+
+// Decode the winning key of window v and publish it: absolute index (:60),
+// clamp (:61), response, next guess, optional trajectory slot.
+__device__ __forceinline__ void publish_result(const WinArgs &a, int v, unsigned long long key,
+                                               int wy0, int wx0)
+{
+    unsigned int idx = key_index(key);
+    int xx = (int)(idx / (unsigned int)a.wr);
+    int yy = (int)(idx - (unsigned int)xx * (unsigned int)a.wr);
+    int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;
+    int ci = min(max(raw_i, 1), a.H), cj = min(max(raw_j, 1), a.W);
+    float resp = key_value(key);
+    int4 p = make_int4(ci, cj, raw_i, raw_j);
+    a.out_pos[v] = p;
+    a.out_resp[v] = resp;
+    if (a.next_guess) a.next_guess[v] = make_int2(ci, cj);
+    if (a.traj_pos) { a.traj_pos[v] = p; a.traj_resp[v] = resp; }
+}
+
+size_t generic_smem_bytes(int L, int Lpad);
+cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s);
+
+// Specialised batched kernel: l = 65 (target_width 25), 45×45 window.
+bool window45_supported(const WinArgs &a);
+cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s);
+const char *window45_name();
+
+// fillvalue = mode(frame) (src/PawsomeTracker.jl:47) for n frames.
+// hist: [n][512] unsigned scratch (counts, last positions), zeroed by the launch.
+cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int H, int W, int n,
+                        int pixel, unsigned int *hist, float *fill_out, int *fill_int_out,
+                        cudaStream_t s);
+
+} // namespace pt

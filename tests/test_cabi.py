@@ -1,0 +1,98 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports every
+symbol include/pawsome.h declares, the scalar helpers agree with the oracle,
+and compute entry points fail loudly (no CPU fallback) without a device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pawsome.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"^PT_API\s+[^;(]*?\b(pt_[a-z0-9_]+)\s*\(", src, flags=re.M)))
+
+
+def test_header_declares_expected_surface():
+    syms = declared_symbols()
+    for must in ("pt_batch_create", "pt_batch_step", "pt_batch_track_host", "pt_batch_track_device",
+                 "pt_tracker_create", "pt_tracker_step", "pt_tracker_step_host", "pt_batch_compute_fill",
+                 "pt_last_error", "pt_device_count"):
+        assert must in syms
+    assert len(syms) >= 30
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (pt_[a-z0-9_]+)", out))
+    missing = [s for s in declared_symbols() if s not in exported]
+    assert not missing, f"declared in pawsome.h but not exported: {missing}"
+    # and the ctypes binding covers the same set
+    assert set(pkg._lib.SIGNATURES) == set(declared_symbols())
+
+
+def test_header_is_plain_c():
+    """The boundary must compile as C (no torch / C++ types in the signatures)."""
+    code = '#include "pawsome.h"\nint main(void){return pt_version()==0;}\n'
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                       input=code, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_scalar_helpers_match_oracle(pkg, oracle):
+    for tw in (3, 7.5, 10, 25, 33, 100, 180):
+        assert pkg.kernel_len(tw) == oracle.kernel_len(tw)
+        assert pkg.guess_window_size(tw) == oracle.default_window(tw)
+        assert pkg.get_sigma(tw) == oracle.sigma(tw)
+    assert pkg.lib.pt_version() == 100
+
+
+@pytest.mark.parametrize("tw,darker", [(25, True), (25, False), (100, True), (10, False)])
+def test_fp32_factors_are_the_rounded_oracle_factors(pkg, oracle, tw, darker):
+    rp, rm, cp, cm = pkg.factors_f32(tw, darker)
+    gp, gm = oracle.factors(tw)
+    d = -1.0 if darker else 1.0
+    np.testing.assert_array_equal(rp, gp.astype(np.float32))
+    np.testing.assert_array_equal(rm, gm.astype(np.float32))
+    np.testing.assert_array_equal(cp, (d * gp).astype(np.float32))
+    np.testing.assert_array_equal(cm, (-d * gm).astype(np.float32))
+
+
+def test_bad_arguments_are_reported(pkg):
+    h = C.c_void_p()
+    lib = pkg.lib
+    assert lib.pt_kernel_len(-1.0) == -1 and "target_width" in pkg._lib.last_error()
+    assert lib.pt_batch_create(0, 10, 10, 25.0, 45, 45, 1, 0, 0, C.byref(h)) == -1
+    assert lib.pt_batch_create(1, 10, 10, 25.0, 45, 45, 1, 7, 0, C.byref(h)) == -1       # unknown pixel type
+    assert lib.pt_batch_create(1, 10, 10, float("nan"), 45, 45, 1, 0, 0, C.byref(h)) == -1
+    assert lib.pt_batch_create(1, 10, 10, 25.0, 0, 45, 1, 0, 0, C.byref(h)) == -1
+    assert lib.pt_batch_step(None, None, None, None, None) == -1
+    assert lib.pt_tracker_step(None, 1, 1, None, None, None) == -1
+    lib.pt_batch_destroy(None)      # no-ops
+    lib.pt_tracker_destroy(None)
+
+
+def test_no_cpu_fallback_without_device(pkg):
+    """Without a usable GPU every compute entry point must fail with PT_ERR_CUDA."""
+    if pkg.lib.pt_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    rc = pkg.lib.pt_batch_create(1, 64, 64, 25.0, 45, 45, 1, 0, 0, C.byref(h))
+    assert rc == -2 and not h.value
+    with pytest.raises(pkg.PawsomeError):
+        pkg.Tracker(np.zeros((64, 64), np.uint8), 25, (45, 45), True)
+
+
+def test_product_path_never_imports_oracle():
+    """Nothing under the package or the C sources may reference oracle/."""
+    pkgdir = os.path.join(ROOT, "pawsometracker.jl_b200")
+    for dp, _, fs in os.walk(pkgdir):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "pawsome_oracle" not in txt, f

@@ -1,0 +1,84 @@
+"""CPU tests of the host-side mirror of the reference interface (no device):
+window-size conventions, start-location forms, resampling, timestamps, the
+synthetic-video recipe."""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+
+def test_window_size_helpers(pkg):
+    # fix_window_size: (w, h) → (h, w); l → (l, l)   (src/PawsomeTracker.jl:70-72)
+    assert pkg.fix_window_size((30, 50)) == (50, 30)
+    assert pkg.fix_window_size(45) == (45, 45)
+    assert pkg.guess_window_size(25) == 45 and pkg.guess_window_size(100) == 173
+
+
+class _V:
+    def __init__(self, sar):
+        self.sar = Fraction(sar)
+
+
+def test_get_guess_three_forms(pkg):
+    img = np.zeros((1080, 1920), np.uint8)
+    assert pkg.get_guess(None, _V(1), img) == (540, 960)                          # missing → size .÷ 2 (:86-90)
+    assert pkg.get_guess(pkg.CartesianIndex(7, 9), _V(2), img) == (7, 9)         # raw index, no SAR (:74-77)
+    assert pkg.get_guess((101, 50), _V(2), img) == (50, 50)                      # 50.5 → 50 (ties to even) (:79-84)
+    assert pkg.get_guess((103, 50), _V(2), img) == (50, 52)                      # 51.5 → 52
+    assert pkg.get_guess((100, 40), _V(Fraction(4, 3)), img) == (40, 75)
+
+
+def test_resampling_indices(pkg):
+    from pawsometracker_jl_b200.api import _Resampled
+    vid = pkg.ArrayVideo([np.full((4, 4), k, np.uint8) for k in range(50)], fps=10.0)
+    r = _Resampled(vid, start=1.0, t=2.0, fps=5.0)       # source frames 10, 12, 14, … ; 10 output frames
+    got = []
+    while not r.eof():
+        got.append(int(r.read()[0, 0]))
+    assert got == list(range(10, 30, 2))
+    r = _Resampled(vid, start=4.0, t=100.0, fps=10.0)    # runs into the end of the source
+    n = 0
+    while not r.eof():
+        r.read(); n += 1
+    assert n == 10
+
+
+def test_partition_overlaps_by_one(pkg):
+    parts = pkg.my_partition(241, 3)                      # test/test-basic-test.jl:43-49
+    assert parts[0][0] == 0 and parts[-1][1] == 240
+    for (a0, a1), (b0, b1) in zip(parts, parts[1:]):
+        assert a1 == b0
+    assert pkg.my_partition(10, 1) == [(0, 9)]
+
+
+def test_spiral_recipe(pkg):
+    tra = pkg.spiral(40.0, 241, (50, 50), seed=0)
+    assert tra.shape == (241, 2) and tuple(tra[0]) == (50, 50)
+    # uniform arc length: consecutive points are ~equidistant (jitter σ=1 per axis)
+    d = np.linalg.norm(np.diff(tra, axis=0), axis=1)
+    assert d.max() < 12 and np.abs(tra - 50).max() <= 40 + 6
+    np.testing.assert_array_equal(tra, pkg.spiral(40.0, 241, (50, 50), seed=0))   # seeded
+    assert not np.array_equal(tra, pkg.spiral(40.0, 241, (50, 50), seed=1))
+    ts, tr = pkg.build_trajectory(40.0, 24, (50, 50))
+    assert len(ts) == 241 == len(tr) and ts[-1] == 10.0
+
+
+def test_synthetic_video_frames(pkg):
+    v = pkg.make_video(H=100, W=100, target_width=10, darker_target=True, start_ij=(50, 50))
+    f = v.frame(0)
+    assert f.dtype == np.uint8 and f.shape == (100, 100)
+    assert f[49, 49] == 0 and f[0, 0] == 128 and (f == 0).sum() == 81           # filled disk of radius 5
+    v2 = pkg.make_video(H=100, W=200, target_width=10, darker_target=False, start_ij=(50, 100), sar=2)
+    f2 = v2.frame(0)
+    assert f2.shape == (100, 100) and f2[49, 49] == 255 and v2.stored_centre(0) == (50, 50)
+
+
+def test_segment_length_mismatch_asserts(pkg):
+    v = pkg.make_video()
+    with pytest.raises(AssertionError, match="Array length mismatch"):
+        pkg.track_segments([v, v], start=[0.0], stop=[1.0, 1.0], start_location=[None, None])
+
+
+def test_diagnostics_are_out_of_scope(pkg):
+    with pytest.raises(NotImplementedError):
+        pkg.track(pkg.make_video(), diagnostic_file="x.mp4")
