@@ -139,6 +139,7 @@ struct pt_batch {
     int *d_fill_i = nullptr;
     bool fill_set = false;
     std::vector<int> h_fill;
+    std::vector<float> h_taps;           // host copy: row narrow | row wide | col narrow | col wide, each L
     int2 *d_guess = nullptr;
     bool guess_set = false;
     int2 *d_center = nullptr;            // crop-mode guess: centre of the footprint
@@ -193,6 +194,8 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     a.keys = b->d_keys; a.counters = b->d_counters;
     a.out_pos = b->d_pos; a.out_resp = b->d_resp;
     a.next_guess = nullptr; a.traj_pos = nullptr; a.traj_resp = nullptr; a.map_out = nullptr;
+    a.T = 1; a.step_stride = 0;
+    a.h_taps = b->h_taps.data();
     (void)nwin;
     return a;
 }
@@ -374,6 +377,10 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     make_taps(tw, b->darker, pixel, rp, rm, cp, cm);
     std::vector<float2> trow(Lpad, make_float2(0.f, 0.f)), tcol(Lpad, make_float2(0.f, 0.f));
     for (int k = 0; k < L; ++k) { trow[k] = make_float2(rp[k], rm[k]); tcol[k] = make_float2(cp[k], cm[k]); }
+    b->h_taps.resize(4 * (size_t)L);
+    for (int k = 0; k < L; ++k) {
+        b->h_taps[k] = rp[k]; b->h_taps[L + k] = rm[k]; b->h_taps[2 * L + k] = cp[k]; b->h_taps[3 * L + k] = cm[k];
+    }
 
     int rc = PT_OK;
     auto cu = [&](cudaError_t e, const char *what) {
@@ -407,7 +414,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     }
     if (rc != PT_OK) { pt_batch_destroy(b); return rc; }
     b->h_fill.assign(n, 0);
-    b->use45 = true;
+    b->use45 = getenv("PT_DISABLE_WINDOW45") == nullptr;   // debugging/parity knob: force the generic kernel
     *out = b;
     return PT_OK;
 }
@@ -546,6 +553,16 @@ int pt_batch_track_device_async(pt_batch *b, const void *dev_base, size_t step_s
     rc = b->d_traj_resp.ensure(sizeof(float) * (size_t)b->n * T); if (rc) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : b->stream;
     const size_t es = px_size(b->pixel);
+    {
+        // the specialised kernel chains all T steps inside one launch (one CTA per video)
+        pt::WinArgs a = make_args(b, dev_base, frame_stride, pitch, b->H, b->W, b->d_guess, b->n);
+        if (b->use45 && pt::window45_supported(a)) {
+            a.next_guess = b->d_guess;
+            a.traj_pos = (int4 *)b->d_traj_pos.p; a.traj_resp = (float *)b->d_traj_resp.p;
+            a.T = T; a.step_stride = step_stride;
+            return launch_step(b, a, b->n, s);
+        }
+    }
     for (int t = 0; t < T; ++t) {
         const void *frames = (const char *)dev_base + (size_t)t * step_stride * es;
         pt::WinArgs a = make_args(b, frames, frame_stride, pitch, b->H, b->W, b->d_guess, b->n);
@@ -829,7 +846,7 @@ const char *pt_batch_kernel_name(const pt_batch *b)
     if (!b) return "";
     pt::WinArgs a;
     memset(&a, 0, sizeof a);
-    a.wr = b->wr; a.wc = b->wc; a.L = b->L; a.w = b->w;
+    a.wr = b->wr; a.wc = b->wc; a.L = b->L; a.w = b->w; a.h_taps = b->h_taps.data();
     if (b->use45 && pt::window45_supported(a)) return pt::window45_name();
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
 }

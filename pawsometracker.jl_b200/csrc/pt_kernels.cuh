@@ -36,6 +36,11 @@ struct WinArgs {
     int4 *traj_pos;            // optional [n] trajectory slot of this step
     float *traj_resp;          // optional [n]
     float *map_out;            // optional response maps, [n][wr*wc] row-major (parity instrumentation)
+    // chained steps in one launch (specialised kernel only): step t reads
+    // frames + t*step_stride and writes trajectory slot t (traj_* then hold [T][n])
+    int T;
+    size_t step_stride;
+    const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
 };
 
 // Orderable packing of (response, column-major index): max key = largest

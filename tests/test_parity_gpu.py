@@ -86,6 +86,21 @@ def test_config1_window_parity(gpu_pkg, oracle, cy, cx, guess):
     check_step(gpu_pkg, oracle, f, 25, True, (45, 45), guess)
 
 
+def test_generic_kernel_on_default_geometry(gpu_pkg, oracle, monkeypatch):
+    """The 45x45 / l=65 geometry normally dispatches to dog_window45_argmax; force the
+    generic streaming kernel on the same frames so both stay parity-checked."""
+    f = disk_frame(480, 640, 200, 300, 12)
+    b = gpu_pkg.TrackerBatch(1, f.shape, 25, (45, 45), True)
+    assert b.kernel_name == "dog_window45_argmax"
+    b.close()
+    monkeypatch.setenv("PT_DISABLE_WINDOW45", "1")
+    b = gpu_pkg.TrackerBatch(1, f.shape, 25, (45, 45), True)
+    assert b.kernel_name.startswith("dog_rect_argmax_generic")
+    b.close()
+    check_step(gpu_pkg, oracle, f, 25, True, (45, 45), (198, 305))
+    check_step(gpu_pkg, oracle, disk_frame(480, 640, 5, 630, 12), 25, True, (45, 45), (10, 625))
+
+
 @pytest.mark.parametrize("tw,ws,darker", [
     (10, (21, 21), True), (10, (21, 33), False), (7, (15, 15), True), (33, (61, 61), True),
     (25, (44, 46), True), (25, (1, 1), True), (25, (91, 31), False), (40, (73, 73), True),
