@@ -218,7 +218,7 @@ void decompose(pt::WinArgs &a, int nwin)
 int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
 {
     cudaError_t e;
-    if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a)) {
+    if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel)) {
         e = pt::launch_window45(a, nwin, b->pixel, s);
     } else {
         decompose(a, nwin);
@@ -556,7 +556,7 @@ int pt_batch_track_device_async(pt_batch *b, const void *dev_base, size_t step_s
     {
         // the specialised kernel chains all T steps inside one launch (one CTA per video)
         pt::WinArgs a = make_args(b, dev_base, frame_stride, pitch, b->H, b->W, b->d_guess, b->n);
-        if (b->use45 && pt::window45_supported(a)) {
+        if (b->use45 && pt::window45_supported(a, b->pixel)) {
             a.next_guess = b->d_guess;
             a.traj_pos = (int4 *)b->d_traj_pos.p; a.traj_resp = (float *)b->d_traj_resp.p;
             a.T = T; a.step_stride = step_stride;
@@ -675,7 +675,7 @@ void lane_worker(HostTrack *ht, pt_lane *ln)
             a.keys = b->d_keys + ln->v0; a.counters = b->d_counters + ln->v0;
             a.out_pos = b->d_pos + ln->v0; a.out_resp = b->d_resp + ln->v0;
             cudaError_t le;
-            if (b->use45 && pt::window45_supported(a)) le = pt::launch_window45(a, nl, b->pixel, ln->stream);
+            if (b->use45 && pt::window45_supported(a, b->pixel)) le = pt::launch_window45(a, nl, b->pixel, ln->stream);
             else { decompose(a, nl); le = pt::launch_generic(a, nl, b->pixel, ln->stream); }
             e = le;
         }
@@ -847,7 +847,7 @@ const char *pt_batch_kernel_name(const pt_batch *b)
     pt::WinArgs a;
     memset(&a, 0, sizeof a);
     a.wr = b->wr; a.wc = b->wc; a.L = b->L; a.w = b->w; a.h_taps = b->h_taps.data();
-    if (b->use45 && pt::window45_supported(a)) return pt::window45_name();
+    if (b->use45 && pt::window45_supported(a, b->pixel)) return pt::window45_name();
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
 }
 

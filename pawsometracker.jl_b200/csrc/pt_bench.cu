@@ -4,6 +4,7 @@
 #include "../../include/pawsome.h"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include "pt_kernels.cuh"
 
 namespace {
 
@@ -98,6 +99,13 @@ PT_API int pt_measure_fp32_peak(int device, int packed, int reps, double *tflops
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(out);
     *tflops = best;
+    return PT_OK;
+}
+
+// Profiling aid: phase timestamps of dog_window45_argmax go to dev_buf ([n][T][6] int64), NULL = off.
+PT_API int pt_debug_window45_timing(void *dev_buf)
+{
+    pt::window45_set_debug((long long *)dev_buf);
     return PT_OK;
 }
 

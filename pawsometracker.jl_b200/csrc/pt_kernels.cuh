@@ -86,9 +86,10 @@ size_t generic_smem_bytes(int L, int Lpad);
 cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s);
 
 // Specialised batched kernel: l = 65 (target_width 25), 45×45 window.
-bool window45_supported(const WinArgs &a);
+bool window45_supported(const WinArgs &a, int pixel);
 cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s);
 const char *window45_name();
+void window45_set_debug(long long *dev_buf);   // phase-timestamp buffer [n][T][6] (profiling aid), nullptr = off
 
 // fillvalue = mode(frame) (src/PawsomeTracker.jl:47) for n frames.
 // hist: [n][512] unsigned scratch (counts, last positions), zeroed by the launch.
