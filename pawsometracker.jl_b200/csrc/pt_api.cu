@@ -5,6 +5,8 @@
 #include "../../include/pawsome.h"
 #include "pt_kernels.cuh"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -108,6 +110,33 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Range of the allocation containing p, through the driver entry point (no libcuda link:
+// the library must still load on a machine without a driver).  false = unknown.
+bool alloc_range(const void *p, const char **base, size_t *size)
+{
+    typedef CUresult (*attr_fn)(void *, CUpointer_attribute, CUdeviceptr);
+    static attr_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (attr_fn)sym;
+        else
+            cudaGetLastError();
+    }
+    if (!fn) return false;
+    CUdeviceptr start = 0;
+    size_t sz = 0;
+    if (fn(&start, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS) return false;
+    if (fn(&sz, CU_POINTER_ATTRIBUTE_RANGE_SIZE, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS) return false;
+    *base = (const char *)(uintptr_t)start;
+    *size = sz;
+    return sz > 0;
+}
+
 bool is_pinned_or_device(const void *p)
 {
     cudaPointerAttributes at;
@@ -157,7 +186,8 @@ struct pt_batch {
     const void *bound_base = nullptr;
     size_t bound_stride = 0, bound_pitch = 0;
     // trajectory buffer for chained steps
-    DevBuf d_traj_pos, d_traj_resp, d_map;
+    DevBuf d_traj_pos, d_traj_resp, d_map, d_ptrs;
+    PinnedBuf h_traj, h_ptrs;
     PinnedBuf h_stage[2], h_out;
     std::vector<pt_lane> lanes;
     long long launches = 0;
@@ -196,6 +226,7 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     a.next_guess = nullptr; a.traj_pos = nullptr; a.traj_resp = nullptr; a.map_out = nullptr;
     a.T = 1; a.step_stride = 0;
     a.h_taps = b->h_taps.data();
+    a.frame_ptrs = nullptr;
     (void)nwin;
     return a;
 }
@@ -438,6 +469,7 @@ void pt_batch_destroy(pt_batch *b)
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
     }
     b->d_traj_pos.release(); b->d_traj_resp.release(); b->d_map.release(); b->h_out.release();
+    b->d_ptrs.release(); b->h_traj.release(); b->h_ptrs.release();
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     delete b;
@@ -772,7 +804,56 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
         return PT_OK;
     }
 
-    // footprint streaming
+    // footprint streaming, zero-copy variant: when every frame is page-locked (pinned) host memory and
+    // the geometry dispatches to the chained kernel, the kernel reads each window's footprint straight
+    // from the host frame over PCIe and writes every step's result straight into pinned host memory —
+    // the whole frame loop (:163-169) is one launch, with no host gather and no per-step round trip.
+    if (!getenv("PT_NO_ZEROCOPY")) {
+        pt::WinArgs probe = make_args(b, nullptr, 0, pitch, b->H, b->W, b->d_guess, b->n);
+        probe.frame_ptrs = reinterpret_cast<const void *const *>(1);   // "pointer table" marker for the support check
+        bool ok = b->use45 && pt::window45_supported(probe, b->pixel);
+        const size_t cnt = n * (size_t)T;
+        if (ok) { rc = b->h_ptrs.ensure(cnt * sizeof(void *)); if (rc) return rc; }
+        const void **hp = (const void **)b->h_ptrs.p;
+        // host address range [rb, rb+rs) already known to be pinned, and its device alias rd
+        const char *rb = nullptr, *rd = nullptr; size_t rs = 0;
+        for (size_t i = 0; ok && i < cnt; ++i) {
+            const char *f = (const char *)frames[i];
+            if (!f) return fail(PT_ERR_ARG, "frames[%zu] is NULL", i);
+            if (!(rb && f >= rb && f < rb + rs)) {
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, f) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+                if (at.type != cudaMemoryTypeHost || !at.devicePointer) { ok = false; break; }
+                const char *base = nullptr; size_t size = 0;
+                if (alloc_range(f, &base, &size) && f >= base && f < base + size) {
+                    rb = base; rs = size; rd = (const char *)at.devicePointer - (f - base);
+                } else {
+                    rb = f; rs = 1; rd = (const char *)at.devicePointer;      // this pointer only
+                }
+            }
+            hp[i] = rd + (f - rb);
+            if (b->pixel == PT_PIX_U8 && ((uintptr_t)hp[i] & 3u) != 0) { ok = false; break; }
+        }
+        if (ok) {
+            rc = b->d_ptrs.ensure(cnt * sizeof(void *)); if (rc) return rc;
+            rc = b->h_traj.ensure(cnt * 20); if (rc) return rc;
+            int4 *hpos = (int4 *)b->h_traj.p;
+            float *hresp = (float *)((char *)b->h_traj.p + cnt * 16);
+            CU(cudaMemcpyAsync(b->d_ptrs.p, hp, cnt * sizeof(void *), cudaMemcpyHostToDevice, b->stream));
+            pt::WinArgs a = make_args(b, nullptr, 0, pitch, b->H, b->W, b->d_guess, b->n);
+            a.frame_ptrs = (const void *const *)b->d_ptrs.p;
+            a.next_guess = b->d_guess;
+            a.traj_pos = hpos; a.traj_resp = hresp;           // pinned + mapped: zero-copy stores, one per step
+            a.T = T;
+            rc = launch_step(b, a, b->n, b->stream); if (rc) return rc;
+            CU(cudaStreamSynchronize(b->stream));
+            for (size_t i = 0; i < cnt; ++i) { out_ij[2 * i] = hpos[i].x; out_ij[2 * i + 1] = hpos[i].y; if (out_resp) out_resp[i] = hresp[i]; }
+            return PT_OK;
+        }
+    }
+
+    // footprint streaming through pinned staging (pageable host frames, or a geometry the chained kernel
+    // does not cover)
     rc = ensure_lanes(b); if (rc) return rc;
     HostTrack ht;
     ht.b = b; ht.frames = frames; ht.T = T; ht.pitch = pitch; ht.out_ij = out_ij; ht.out_resp = out_resp;

@@ -40,6 +40,8 @@ struct WinArgs {
     // frames + t*step_stride and writes trajectory slot t (traj_* then hold [T][n])
     int T;
     size_t step_stride;
+    const void *const *frame_ptrs;  // optional DEVICE array [T][n] of frame base pointers (overrides frames/strides):
+                               // used for zero-copy reads of pinned host frames (specialised kernel only)
     const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
 };
 

@@ -54,6 +54,7 @@ struct Taps45 {
 struct Args45 {
     const void *frames;                 // frame of window 0 at step 0
     size_t frame_stride, step_stride;   // elements
+    const void *const *frame_ptrs;      // optional [T][n] frame pointers (zero-copy pinned host frames)
     int pitch, H, W;
     const float *fill;
     const int2 *guess;                  // [n] start guess (1-based)
@@ -213,7 +214,9 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             dbg[0] = (t == 0) ? (long long)smid : (long long)gt;   // t>0: wall-clock ns at frame start
             dbg[1] = clock64();
         }
-        const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)t * a.step_stride + (size_t)v * a.frame_stride;
+        const PixT *frame = a.frame_ptrs
+            ? reinterpret_cast<const PixT *>(a.frame_ptrs[(size_t)t * a.n + v])
+            : reinterpret_cast<const PixT *>(a.frames) + (size_t)t * a.step_stride + (size_t)v * a.frame_stride;
         const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);   // window origin, 0-based
         const int fy0 = wy0 - HW, fx0 = wx0 - HW;                        // footprint origin
 
@@ -221,7 +224,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
 
         // ---- warm L2 with everything the NEXT step can touch: its window centre is inside this
         // step's window, so its footprint lies within ±22 px of this one (153 rows × ≤3 lines).
-        if (t + 1 < a.T) {
+        if (t + 1 < a.T && !a.frame_ptrs) {                      // (host frames are not cached in L2)
             const PixT *nframe = frame + a.step_stride;
             constexpr int PR = FR + WR - 1;                      // 153 rows
             const int py0 = fy0 - WR / 2, pxb = (fx0 - WC / 2) * (int)sizeof(PixT);
@@ -347,6 +350,7 @@ void window45_set_debug(long long *dev_buf) { g_dbg = dev_buf; }
 bool window45_supported(const WinArgs &a, int pixel)
 {
     if (!(a.L == L && a.wr == WR && a.wc == WC && !a.rect_mode && a.map_out == nullptr)) return false;
+    if (pixel == 0 && a.frame_ptrs) return (a.pitch & 3) == 0 && a.pitch >= ((a.W + 3) & ~3);   // caller checked the pointers
     if (pixel == 0 && a.frames) {
         // the u8 staging path loads aligned 32-bit words
         const bool aligned = ((reinterpret_cast<uintptr_t>(a.frames) | (uintptr_t)a.pitch | (uintptr_t)a.frame_stride |
@@ -377,6 +381,7 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
     cudaError_t e;
     Args45 k;
     k.frames = a.frames; k.frame_stride = a.frame_stride; k.step_stride = a.step_stride;
+    k.frame_ptrs = a.frame_ptrs;
     k.pitch = a.pitch; k.H = a.H; k.W = a.W; k.fill = a.fill; k.guess = a.guess;
     k.T = a.T > 0 ? a.T : 1;
     {

@@ -316,6 +316,41 @@ def test_batch_equals_singles_and_all_paths_agree(gpu_pkg, oracle):
         np.testing.assert_array_equal(ij_fp[:, v], ref)
 
 
+def test_zero_copy_pinned_host_frames(gpu_pkg, oracle, monkeypatch):
+    """Pinned host frames: the chained kernel reads footprints over PCIe (zero-copy).  Must equal
+    the staged footprint path (pageable frames) and the oracle loop, incl. windows leaving the frame."""
+    import torch
+    n, T, H, W = 5, 12, 200, 256
+    vids = [gpu_pkg.make_video(H=H, W=W, target_width=25, start_ij=(100, 128), seconds=10.0, fps=24.0, seed=10 + s)
+            for s in range(n)]
+    steps = [[v.frame(t) for v in vids] for t in range(T)]
+    steps[3][0][:] = np.roll(steps[3][0], (-70, -100), axis=(0, 1))      # throw video 0 towards a corner
+    pinned = torch.empty((T, n, H, W), dtype=torch.uint8, pin_memory=True)
+    pnp = pinned.numpy()
+    for t in range(T):
+        for v in range(n):
+            pnp[t, v] = steps[t][v]
+    start = np.tile([100, 128], (n, 1))
+    with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
+        b.set_frames(steps[0]); b.compute_fill()
+        b.set_guess(start)
+        ij_pageable, r_pageable = b.track_host(steps, mode="footprint")
+        b.set_guess(start)
+        lc = b.launch_count
+        ij_zc, r_zc = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+        assert b.launch_count - lc == 1, "pinned frames must take the single-launch zero-copy path"
+        nxt, _ = b.step(None)                                          # chain state was left on the device
+        monkeypatch.setenv("PT_NO_ZEROCOPY", "1")
+        b.set_guess(start)
+        ij_staged, _ = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+    np.testing.assert_array_equal(ij_zc, ij_pageable)
+    np.testing.assert_array_equal(ij_zc, ij_staged)
+    np.testing.assert_array_equal(r_zc, r_pageable)
+    for v in range(n):
+        ref, _ = oracle_track(oracle, [s[v] for s in steps], 25, True, (45, 45), (100, 128))
+        np.testing.assert_array_equal(ij_zc[:, v], ref)
+
+
 def test_track_autodetect_and_batch_api(gpu_pkg, oracle):
     """start_location = missing → auto-detect then track; track_batch == per-video track."""
     vids = [gpu_pkg.make_video(H=240, W=320, target_width=25, start_ij=(120, 160), seconds=10.0, fps=24.0, seed=s)
