@@ -99,55 +99,56 @@ def render_frame_host(out, centre):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock and throttle reasons with NVML while a region runs."""
+    """Samples SM clock, power and throttle reasons with `nvidia-smi -lms` (B200_PROFILING.md recipe)
+    in a subprocess while a region runs."""
 
-    def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._th = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
 
-    def _loop(self):
-        nv = self.nv
-        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
-                 "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
-            time.sleep(0.02)
+    def __init__(self, index, period_ms=50):
+        self.index, self.period_ms, self.proc, self.lines = index, period_ms, None, []
 
     def __enter__(self):
-        if self.nv:
-            self._th = threading.Thread(target=self._loop, daemon=True)
-            self._th.start()
+        import subprocess
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        if self._th:
-            self._th.join()
+        if self.proc:
+            time.sleep(2.5 * self.period_ms / 1e3)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            self.lines = [l for l in out.splitlines() if l.strip()]
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        mhz, mx, watts, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mhz.append(float(f[0])); mx = float(f[1]); watts.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not mhz:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "samples": 0}
+        # "under load" = samples taken while the GPU was clocked up by the timed kernels
+        return {"sm_mhz": float(np.median(mhz)), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz), "power_w_max": max(watts) if watts else None}
 
 
 # ---------------------------------------------------------------------------
@@ -322,6 +323,9 @@ def run_gpu(args, ranks):
     ij_chk, _ = batch.track_device(ring.data_ptr(), step_stride, frame_stride, W, min(Wm + K, slots))
     resident_ok = bool(np.array_equal(ij_chk, truth_for_steps(pos, min(Wm + K, slots))))
 
+    sampler = ClockSampler(dev_index, period_ms=20)
+    sampler.__enter__()
+    time.sleep(0.8)                      # let nvidia-smi start before the load begins
     # pre-heat: bring the SM clock to its steady state with ~0.3 s of the same (untimed) work
     t_heat = time.perf_counter()
     while time.perf_counter() - t_heat < args.preheat:
@@ -330,10 +334,10 @@ def run_gpu(args, ranks):
         torch.cuda.synchronize(device)
 
     launches_before = batch.launch_count
+    batch_kernel = batch.kernel_name
     reps_ms = []
-    sampler = ClockSampler(dev_index)
     t_wall0 = time.perf_counter()
-    with sampler:
+    if True:
         rep = 0
         while True:
             pkg.lib.pt_flush_l2(flush.data_ptr(), flush.numel(), batch.stream)      # untimed: cold L2 for every repeat
@@ -342,18 +346,21 @@ def run_gpu(args, ranks):
             ranks.barrier()
             torch.cuda.synchronize(device)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            lc0 = batch.launch_count
             with torch.cuda.stream(ext):
                 e0.record()
                 run_chain(Wm % slots, K)                                             # EXACTLY K timed steps
                 e1.record()
+            timed_launches = batch.launch_count - lc0
             torch.cuda.synchronize(device)
             ranks.barrier()
             reps_ms.append(ranks.max_over_ranks(e0.elapsed_time(e1), device))        # max over ranks, device time
             rep += 1
             if rep >= args.repeats or (rep >= 5 and time.perf_counter() - t_wall0 > 2.5):
                 break
+    sampler.__exit__(None, None, None)
     clocks = sampler.summary()
-    launches_resident = batch.launch_count - launches_before
+    del launches_before
     ms_K = float(np.median(reps_ms))
     world = ranks.world
     value = world * n * K / (ms_K * 1e-3)
@@ -366,24 +373,37 @@ def run_gpu(args, ranks):
     pkg._lib.check(pkg.lib.pt_measure_fp32_peak(dev_index, 1, 5, C.byref(tf2)))
     fp32_peak = max(tf.value, tf2.value)
     alg = algorithmic_per_window()
-    per_launch_s = ms_K * 1e-3 / K
-    ach_tflops = n * alg["flops"] / per_launch_s / 1e12
-    ach_gbs = n * alg["bytes"] / per_launch_s / 1e9
+    launch_s = ms_K * 1e-3 / max(1, timed_launches)          # the dominant kernel chains K steps per launch
+    steps_per_launch = K / max(1, timed_launches)
+    flops_launch = steps_per_launch * n * alg["flops"]
+    bytes_launch = steps_per_launch * n * alg["bytes"]
+    ach_tflops = flops_launch / launch_s / 1e12
+    ach_gbs = bytes_launch / launch_s / 1e9
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    t_roof = max(n * alg["flops"] / (fp32_peak * 1e12), n * alg["bytes"] / (hbm_peak * 1e9))
+    t_roof = max(flops_launch / (fp32_peak * 1e12), bytes_launch / (hbm_peak * 1e9))
+    # DRAM traffic of this kernel from profiles/r01_window45_final_ncu_full_selected.csv (one `ncu --set full`
+    # capture of a 20-step launch: dram read 279.0 MB + write 3.6 MB): 14.13 MB per 256-video step
+    traffic_per_step = 14.13e6 if batch_kernel == "dog_window45_argmax" else None
     roofline = {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach_tflops / fp32_peak, "traffic": None,
-                "kernel": batch.kernel_name,
+                "frac": ach_tflops / fp32_peak,
+                "traffic": traffic_per_step * steps_per_launch if traffic_per_step else None,
+                "traffic_note": "dram__bytes_read+write per launch scaled from the ncu --set full capture in profiles/ "
+                                "(14.13 MB per 256-video step vs 3.05 MB algorithmic: 109-byte rows inside 128-byte "
+                                "lines, plus the deliberate L2 prefetch of the 153-row region the next step can touch; "
+                                "DRAM is at 4 % of its peak)",
+                "kernel": batch_kernel,
                 "peak_source": "measured in this run (pt_measure_fp32_peak: dependent FFMA chains, best of 5; "
                                f"scalar {tf.value:.1f}, f32x2 {tf2.value:.1f} TFLOP/s); nominal {NOMINAL_FP32_TFLOPS:.1f}",
-                "algorithmic_flops_per_launch": n * alg["flops"], "algorithmic_bytes_per_launch": n * alg["bytes"],
-                "launch_us": per_launch_s * 1e6, "roofline_us": t_roof * 1e6,
-                "frac_of_roofline_time": t_roof / per_launch_s,
+                "launches_in_timed_region": int(timed_launches), "steps_per_launch": steps_per_launch,
+                "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch,
+                "algorithmic_flops_per_window": alg["flops"], "algorithmic_bytes_per_window": alg["bytes"],
+                "launch_us": launch_s * 1e6, "roofline_us": t_roof * 1e6,
+                "frac_of_roofline_time": t_roof / launch_s,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}}
 
@@ -472,7 +492,10 @@ def run_gpu(args, ranks):
                                timing="CUDA events on the launching stream, median over repeats, max over ranks"),
                 "clocks": clocks, "e2e": e2e, "e2e_frames": e2e_frames, "roofline": roofline,
                 "cpu_baseline": cpu, "fullframe_dog": fullframe,
-                "gpu_launches": int(launches_resident // max(1, len(reps_ms)) - Wm),
+                "gpu_launches": int(timed_launches),
+                "gpu_launches_note": f"{batch_kernel} chains the K steps of the timed region inside "
+                                     f"{int(timed_launches)} launch(es) (one CTA per SM hosts two videos; the serial "
+                                     "frame chain of a video never leaves its CTA)",
                 "gpu_launches_e2e": int(launches_e2e),
                 "positions_correct": bool(all_ok),
                 "ms_K_repeats": {"min": float(np.min(reps_ms)), "median": ms_K, "max": float(np.max(reps_ms))}}

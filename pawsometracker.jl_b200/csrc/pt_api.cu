@@ -152,7 +152,7 @@ struct pt_lane {
     cudaStream_t stream = nullptr;
     PinnedBuf h_crops, h_res;
     DevBuf d_crops;
-    int v0 = 0, v1 = 0;
+    int v0 = 0, v1 = 0, index = 0;
 };
 
 struct pt_batch {
@@ -186,7 +186,7 @@ struct pt_batch {
     const void *bound_base = nullptr;
     size_t bound_stride = 0, bound_pitch = 0;
     // trajectory buffer for chained steps
-    DevBuf d_traj_pos, d_traj_resp, d_map, d_ptrs;
+    DevBuf d_traj_pos, d_traj_resp, d_map, d_ptrs, d_xkeys, d_xcnt;
     PinnedBuf h_traj, h_ptrs;
     PinnedBuf h_stage[2], h_out;
     std::vector<pt_lane> lanes;
@@ -227,15 +227,21 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     a.T = 1; a.step_stride = 0;
     a.h_taps = b->h_taps.data();
     a.frame_ptrs = nullptr;
+    a.xkeys = nullptr; a.xcnt = nullptr;
     (void)nwin;
     return a;
 }
 
 void decompose(pt::WinArgs &a, int nwin)
 {
+    // Strips of 32 output columns; row chunks only where a launch would otherwise leave the GPU
+    // under-occupied.  Each extra chunk repeats 2w footprint rows of the row pass, so chunks are
+    // added until ~kTarget CTAs exist (measured best for the 1080p full-frame shape) and never below
+    // one batch of rows.
+    static int target = 0;
+    if (target == 0) { const char *e = getenv("PT_GENERIC_TARGET"); target = e ? atoi(e) : 4 * 148; if (target < 1) target = 1; }
     a.strips = (a.wc + pt::kTileCols - 1) / pt::kTileCols;
     const int total = nwin * a.strips;
-    const int target = 2 * 148;
     int chunks = 1;
     if (total < target) {
         chunks = (target + total - 1) / total;
@@ -249,9 +255,24 @@ void decompose(pt::WinArgs &a, int nwin)
 int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
 {
     cudaError_t e;
-    if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel)) {
-        e = pt::launch_window45(a, nwin, b->pixel, s);
-    } else {
+    bool done = false;
+    if (b->use45 && !a.rect_mode && !a.map_out) {
+        // preferred: 4 CTAs per window (needs all 4n CTAs co-resident and u8 frames)
+        const size_t slots = (size_t)nwin * (size_t)(a.T > 0 ? a.T : 1);
+        int rc = b->d_xkeys.ensure(slots * sizeof(unsigned long long)); if (rc) return rc;
+        rc = b->d_xcnt.ensure(slots * sizeof(unsigned int)); if (rc) return rc;
+        a.xkeys = (unsigned long long *)b->d_xkeys.p; a.xcnt = (unsigned int *)b->d_xcnt.p;
+        if (pt::window45_quad_supported(a, nwin, b->pixel)) {
+            CU(cudaMemsetAsync(a.xkeys, 0, slots * sizeof(unsigned long long), s));
+            CU(cudaMemsetAsync(a.xcnt, 0, slots * sizeof(unsigned int), s));
+            e = pt::launch_window45_quad(a, nwin, s);
+            done = true;
+        } else if (pt::window45_supported(a, b->pixel)) {
+            e = pt::launch_window45(a, nwin, b->pixel, s);
+            done = true;
+        }
+    }
+    if (!done) {
         decompose(a, nwin);
         e = pt::launch_generic(a, nwin, b->pixel, s);
     }
@@ -469,7 +490,7 @@ void pt_batch_destroy(pt_batch *b)
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
     }
     b->d_traj_pos.release(); b->d_traj_resp.release(); b->d_map.release(); b->h_out.release();
-    b->d_ptrs.release(); b->h_traj.release(); b->h_ptrs.release();
+    b->d_ptrs.release(); b->h_traj.release(); b->h_ptrs.release(); b->d_xkeys.release(); b->d_xcnt.release();
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     delete b;
@@ -588,7 +609,7 @@ int pt_batch_track_device_async(pt_batch *b, const void *dev_base, size_t step_s
     {
         // the specialised kernel chains all T steps inside one launch (one CTA per video)
         pt::WinArgs a = make_args(b, dev_base, frame_stride, pitch, b->H, b->W, b->d_guess, b->n);
-        if (b->use45 && pt::window45_supported(a, b->pixel)) {
+        if (b->use45 && pt::window45_supported(a, b->pixel)) {   // (the 4-CTA kernel covers a subset of this)
             a.next_guess = b->d_guess;
             a.traj_pos = (int4 *)b->d_traj_pos.p; a.traj_resp = (float *)b->d_traj_resp.p;
             a.T = T; a.step_stride = step_stride;
@@ -744,6 +765,7 @@ int ensure_lanes(pt_batch *b)
         for (int i = 0; i < want; ++i) {
             b->lanes[i].v0 = (int)((long long)b->n * i / want);
             b->lanes[i].v1 = (int)((long long)b->n * (i + 1) / want);
+            b->lanes[i].index = i;
             CU(cudaStreamCreateWithFlags(&b->lanes[i].stream, cudaStreamNonBlocking));
         }
     }
@@ -928,6 +950,9 @@ const char *pt_batch_kernel_name(const pt_batch *b)
     pt::WinArgs a;
     memset(&a, 0, sizeof a);
     a.wr = b->wr; a.wc = b->wc; a.L = b->L; a.w = b->w; a.h_taps = b->h_taps.data();
+    if (b->use45 && b->pixel == PT_PIX_U8 && getenv("PT_ENABLE_QUAD") && a.L == 65 && a.wr == 45 && a.wc == 45 &&
+        b->n <= pt::window45_quad_max_windows())
+        return pt::window45_quad_name();
     if (b->use45 && pt::window45_supported(a, b->pixel)) return pt::window45_name();
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
 }

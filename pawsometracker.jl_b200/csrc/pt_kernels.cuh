@@ -42,6 +42,8 @@ struct WinArgs {
     size_t step_stride;
     const void *const *frame_ptrs;  // optional DEVICE array [T][n] of frame base pointers (overrides frames/strides):
                                // used for zero-copy reads of pinned host frames (specialised kernel only)
+    unsigned long long *xkeys; // [n][T] cross-CTA argmax keys   } exchange scratch of the 4-CTA-per-window kernel,
+    unsigned int *xcnt;        // [n][T] arrival counters        } zeroed by the launcher's caller before each launch
     const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
 };
 
@@ -91,7 +93,14 @@ cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s);
 bool window45_supported(const WinArgs &a, int pixel);
 cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s);
 const char *window45_name();
-void window45_set_debug(long long *dev_buf);   // phase-timestamp buffer [n][T][6] (profiling aid), nullptr = off
+void window45_set_debug(long long *dev_buf);
+long long *window45_debug_ptr();   // phase-timestamp buffer [n][T][6] (profiling aid), nullptr = off
+
+// Second-generation specialised kernel: 4 CTAs per window, u8 frames, cooperative launch.
+bool window45_quad_supported(const WinArgs &a, int n, int pixel);
+int window45_quad_max_windows();
+cudaError_t launch_window45_quad(const WinArgs &a, int n, cudaStream_t s);
+const char *window45_quad_name();
 
 // fillvalue = mode(frame) (src/PawsomeTracker.jl:47) for n frames.
 // hist: [n][512] unsigned scratch (counts, last positions), zeroed by the launch.

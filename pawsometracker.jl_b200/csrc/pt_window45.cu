@@ -1,28 +1,38 @@
 // pt_window45.cu — the batched hot path at the reference's default geometry:
 // target_width = 25 → l = 65 (w = 32), window 45×45 (radii 22), footprint
-// 109×109.  One CTA per (video, window); a launch can chain T time steps of the
-// same videos (frames resident in HBM) because windows of different videos
-// never interact: ij[t] = trckr(ij[t-1]) (src/PawsomeTracker.jl:167) stays
-// inside the CTA, so there is no grid-wide dependency between steps.
+// 109×109.  One CTA evaluates one (video, frame) window at a time; a launch can chain
+// T time steps of the same videos (frames resident in HBM, or pinned on the host)
+// because windows of different videos never interact: ij[t] = trckr(ij[t-1])
+// (src/PawsomeTracker.jl:167) only links consecutive frames of ONE video.
 //
-// Per frame and CTA:
+// Scheduling: one 512-thread CTA per SM hosts TWO independent windows ("halves"), each
+// run by 8 warps that synchronise on their own named barrier.  The warps of the two
+// halves are interleaved over the scheduler slots (warps 0-3 and 8-11 → half 0, warps 4-7
+// and 12-15 → half 1), so each SM sub-partition holds two warps of either window and the
+// slot-order arbitration treats both alike.  (With two separate CTAs per SM the warp
+// scheduler favoured one of them: 13.3 K vs 19.8 K cycles per frame, and the slow one set
+// the launch time.)  Half h of CTA c walks videos c + S·h, c + S·(h+2), … (S = #CTAs) and
+// keeps the guess of its current video in registers from frame to frame: no hand-off.
+//
+// Per window:
 //   stage  109×109 pixels → smem as (pixel − fill), 0 outside the frame
 //          (the PaddedView border, src/PawsomeTracker.jl:48, after subtracting
 //          the constant fill — legal because ΣDoG = 0)
 //   row    both Gaussians for 109 rows × 45 columns.  The factors are
 //          symmetric, so each output is g0·x0 + Σ_d g_d·(x_-d + x_+d): one FADD
 //          feeds ONE packed FFMA2 that advances (narrow, wide) together.
-//          Thread = (row, 9 consecutive columns), 73 shared loads per 585 ops.
+//          Thread = (row, 5 consecutive columns): 31 warp-tasks balance over 8 warps.
 //   col    45×45 outputs, thread = (column, 9 consecutive rows); one FFMA2
 //          advances two vertically adjacent outputs; subtraction and the
 //          darker_target sign are folded into the column taps.
-//   argmax warp shuffles + 9 keys in smem that every thread folds itself: first
+//   argmax warp shuffles + 8 keys in smem that every thread folds itself: first
 //          maximum in column-major order (findmax, :59); clamp (:61).
 //
 // All taps are kernel parameters (constant bank → uniform registers), the loops
 // are fully unrolled, so no tap is ever loaded inside the passes.
 #include "pt_kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace pt {
@@ -35,12 +45,15 @@ constexpr int FR = WR + 2 * HW;         // 109 footprint rows
 constexpr int FC = WC + 2 * HW;         // 109 footprint cols
 constexpr int PIN = 109;                // s_in pitch (floats), odd → row-lanes conflict-free
 constexpr int PM = 45;                  // s_mid pitch (float2), odd → 64-bit row-lane stores conflict-free
-constexpr int R = 9;                    // outputs per thread along the filter direction
+constexpr int R = 9;                    // column pass: outputs per thread along the filter direction
 constexpr int NG = 5;                   // groups of R per 45
-constexpr int ROW_ITEMS = FR * NG;      // 545
-constexpr int COL_ITEMS = WC * NG;      // 225
-constexpr int THREADS = 256;            // 8 warps = 2 per SM sub-partition; row items take 3 rounds, column items 1
+constexpr int COL_ITEMS = WC * NG;      // 225 → 8 warp-tasks on 8 warps
+constexpr int RR = 5;                   // row pass: outputs per thread; 9 groups per row
+constexpr int ROW_ITEMS = FR * (WC / RR);   // 981 → 31 warp-tasks: 4 (or 3) per warp, 98.9 % lane fill
+constexpr int THREADS = 256;            // threads per window: 8 warps = 2 per SM sub-partition; row items take 3 rounds
 constexpr int NWARPS = THREADS / 32;
+constexpr int CTA_THREADS = 2 * THREADS;   // two windows per CTA
+constexpr size_t HALF_SMEM = ((size_t)(FR * PIN + 1) * sizeof(float) + (size_t)FR * PM * sizeof(float2) + 15) & ~(size_t)15;
 
 // Taps as kernel parameters, laid out for packed FP32 (fma.rn.f32x2 → FFMA2):
 //   rt[d]  = (narrow, wide) folded row taps, d = |k − 32| (pixel scale folded in)
@@ -58,15 +71,12 @@ struct Args45 {
     int pitch, H, W;
     const float *fill;
     const int2 *guess;                  // [n] start guess (1-based)
-    int T;
-    int skew_cycles;                    // second-wave CTAs (blockIdx ≥ #SMs) start this many cycles late
-    int num_sms;
-    int warp_rot;                       // logical-warp rotation of second-wave CTAs (sub-partition balance)
+    int T, n;
     int4 *out_pos; float *out_resp;     // [n] last step
     int2 *next_guess;                   // [n] or null
     int4 *traj_pos; float *traj_resp;   // [T][n] or null
-    int n;
-    long long *dbg;                     // optional [n][T][6]: smid, t0, after stage, after row, after col, end (clock64)
+    int skew;                           // 1: half 1 of each CTA starts half a frame late (anti-phase)
+    long long *dbg;                     // optional [n][T][6]: smid|globaltimer, clock64 at start / stage / row / col / end
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
@@ -176,42 +186,51 @@ __device__ __forceinline__ void stage_tile<uint8_t>(const uint8_t *frame, int pi
 
 } // namespace
 
+__device__ __forceinline__ void bar_half(int half)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(THREADS) : "memory");
+}
+
 template <typename PixT>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(CTA_THREADS, 1)
 dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Taps45 tp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *s_in = reinterpret_cast<float *>(smem_raw);                       // [FR][PIN]
-    float2 *s_mid = reinterpret_cast<float2 *>(s_in + FR * PIN + 1);        // [FR][PM] (8-byte aligned: FR*PIN+1 is even)
-    __shared__ unsigned long long s_key[2 * NWARPS];
+    __shared__ unsigned long long s_keys[2][2 * NWARPS];
 
-    const int lane = threadIdx.x & 31;
-    // Logical warp id.  Row items need 18 warp-tasks on 8 warps, so logical warps 0 and 1 (sub-
-    // partitions 0 and 1) carry 3 tasks and the others 2.  The second CTA that lands on an SM
-    // (blockIdx ≥ #SMs with the breadth-first block scheduler) rotates its mapping by two
-    // sub-partitions so the pair loads all four FMA pipes equally (5+4 tasks each).
-    const int warp = ((threadIdx.x >> 5) + (((int)blockIdx.x >= a.num_sms) ? a.warp_rot : 0)) & (NWARPS - 1);
+    // physical warp → (half, logical warp): warps 0-3, 8-11 → half 0; 4-7, 12-15 → half 1
+    const int pw = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = (pw >> 2) & 1;
+    // logical warp 0..7; half 1 is rotated by two sub-partitions so that the warps carrying the
+    // third row-pass task (logical 0 and 1) of the two windows sit on different FMA pipes
+    const int warp = (((pw & 3) + 2 * half) & 3) + 4 * (pw >> 3);
     const int tid = warp * 32 + lane;
-    const int v = blockIdx.x;
+    float *s_in = reinterpret_cast<float *>(smem_raw + half * HALF_SMEM);      // [FR][PIN]
+    float2 *s_mid = reinterpret_cast<float2 *>(s_in + FR * PIN + 1);           // [FR][PM] (8-byte aligned: FR*PIN+1 is even)
+    unsigned long long *s_key = s_keys[half];
+    const int stride = 2 * (int)gridDim.x;
+
+    // Anti-phase start: both halves do identical work per frame, so started together they stay in
+    // lockstep — colliding on the FMA pipes in the row/column passes and leaving them idle while
+    // both stage.  Half 1 therefore starts when half 0 has finished its first row pass (about half
+    // a frame later); equal periods keep the offset.
+    const bool skewed = a.skew && ((int)blockIdx.x + (int)gridDim.x < a.n);
+    if (skewed && half == 1) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory");
+    bool released = !(skewed && half == 0);
+
+  for (int v = (int)blockIdx.x + (int)gridDim.x * half; v < a.n; v += stride) {
     const float fill = a.fill[v];
     int2 g = a.guess[v];
 
-    // Two CTAs share an SM and would otherwise run their phases in lockstep (both staging,
-    // then both fighting for the FMA pipe).  Starting the second-wave CTA part of a frame
-    // late makes one CTA's staging/reduce overlap the other's FMA passes.
-    if (a.skew_cycles > 0 && (int)blockIdx.x >= a.num_sms && a.T > 1) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < a.skew_cycles) { }
-    }
-
     for (int t = 0; t < a.T; ++t) {
+        const unsigned int it = (unsigned int)t;
         long long *dbg = a.dbg ? a.dbg + ((size_t)v * a.T + t) * 6 : nullptr;
         if (dbg && tid == 0) {
             unsigned int smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             unsigned long long gt;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-            dbg[0] = (t == 0) ? (long long)smid : (long long)gt;   // t>0: wall-clock ns at frame start
+            dbg[0] = ((long long)gt << 8) | (long long)(smid & 0xFF);   // wall-clock ns and SM id at window start
             dbg[1] = clock64();
         }
         const PixT *frame = a.frame_ptrs
@@ -227,45 +246,47 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         if (t + 1 < a.T && !a.frame_ptrs) {                      // (host frames are not cached in L2)
             const PixT *nframe = frame + a.step_stride;
             constexpr int PR = FR + WR - 1;                      // 153 rows
+            constexpr int NL = (int)(((FC + WC) * sizeof(PixT) + 127) / 128) + 1;   // 128-byte lines per row (3 for u8)
             const int py0 = fy0 - WR / 2, pxb = (fx0 - WC / 2) * (int)sizeof(PixT);
-            const int line0 = pxb >> 7, nlines = ((pxb + (FC + WC - 1) * (int)sizeof(PixT) - 1) >> 7) - line0 + 1;
-            for (int e = tid; e < PR * nlines; e += THREADS) {
-                const int r = e / nlines, ln = e - r * nlines;
+            const int rowbytes = a.W * (int)sizeof(PixT);
+            for (int e = tid; e < PR * NL; e += THREADS) {
+                const int r = e / NL, ln = e - r * NL;
                 const int Y = py0 + r;
-                const long long off = ((long long)(line0 + ln)) << 7;
-                if (Y >= 0 && Y < a.H && off >= 0 && off < (long long)a.W * (int)sizeof(PixT)) {
+                const int off = ((pxb >> 7) + ln) << 7;
+                if (Y >= 0 && Y < a.H && off >= 0 && off < rowbytes) {
                     const char *ptr = reinterpret_cast<const char *>(nframe + (size_t)Y * a.pitch) + off;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
                 }
             }
         }
-        __syncthreads();
+        bar_half(half);
         if (dbg && tid == 0) dbg[2] = clock64();
 
         // ---- row pass: item = (footprint row f, column group gq); lanes walk rows
 #pragma unroll 1
         for (int item = tid; item < ROW_ITEMS; item += THREADS) {
             const int gq = item / FR, f = item - gq * FR;
-            const float *row = s_in + f * PIN + gq * R;
-            float x[R + 2 * HW];
+            const float *row = s_in + f * PIN + gq * RR;
+            float x[RR + 2 * HW];
 #pragma unroll
-            for (int i = 0; i < R + 2 * HW; ++i) x[i] = row[i];
-            float2 acc[R];                                   // (narrow, wide) per output
+            for (int i = 0; i < RR + 2 * HW; ++i) x[i] = row[i];
+            float2 acc[RR];                                  // (narrow, wide) per output
 #pragma unroll
-            for (int j = 0; j < R; ++j) acc[j] = fmul2(make_float2(x[j + HW], x[j + HW]), tp.rt[0]);
+            for (int j = 0; j < RR; ++j) acc[j] = fmul2(make_float2(x[j + HW], x[j + HW]), tp.rt[0]);
 #pragma unroll
             for (int d = 1; d <= HW; ++d) {
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
+                for (int j = 0; j < RR; ++j) {
                     const float s = x[j + HW - d] + x[j + HW + d];   // exact for u8 frames (integers)
                     acc[j] = ffma2(make_float2(s, s), tp.rt[d], acc[j]);
                 }
             }
-            float2 *dst = s_mid + f * PM + gq * R;
+            float2 *dst = s_mid + f * PM + gq * RR;
 #pragma unroll
-            for (int j = 0; j < R; ++j) dst[j] = acc[j];
+            for (int j = 0; j < RR; ++j) dst[j] = acc[j];
         }
-        __syncthreads();
+        bar_half(half);
+        if (!released) { asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); released = true; }
         if (dbg && tid == 0) dbg[3] = clock64();
 
         // ---- column pass + running argmax: item = (column xq, row group h); lanes walk columns
@@ -313,13 +334,13 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
             key = o > key ? o : key;
         }
-        if (lane == 0) s_key[(t & 1) * NWARPS + warp] = key;
-        __syncthreads();
+        if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
+        bar_half(half);
         if (dbg && tid == 0) dbg[4] = clock64();
         {
-            // every thread folds the 9 warp keys itself (broadcast loads): no serial section and
-            // no second barrier; s_key is double-buffered by step parity
-            const unsigned long long *kk = s_key + (t & 1) * NWARPS;
+            // every thread folds the 8 warp keys itself (broadcast loads): no serial section;
+            // s_key is double-buffered by iteration parity
+            const unsigned long long *kk = s_key + (it & 1) * NWARPS;
             unsigned long long k = kk[0];
 #pragma unroll
             for (int i = 1; i < NWARPS; ++i) k = kk[i] > k ? kk[i] : k;
@@ -335,17 +356,20 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
                     a.out_pos[v] = p; a.out_resp[v] = resp;
                     if (a.next_guess) a.next_guess[v] = make_int2(ci, cj);
                 }
+                if (dbg) dbg[5] = clock64();
             }
             g = make_int2(ci, cj);
         }
-        if (dbg && tid == 0) dbg[5] = clock64();
     }
+    bar_half(half);    // s_key / smem of this half are reused by the next video
+  }
 }
 
 const char *window45_name() { return "dog_window45_argmax"; }
 
 static long long *g_dbg = nullptr;
 void window45_set_debug(long long *dev_buf) { g_dbg = dev_buf; }
+long long *window45_debug_ptr() { return g_dbg; }
 
 bool window45_supported(const WinArgs &a, int pixel)
 {
@@ -384,32 +408,33 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
     k.frame_ptrs = a.frame_ptrs;
     k.pitch = a.pitch; k.H = a.H; k.W = a.W; k.fill = a.fill; k.guess = a.guess;
     k.T = a.T > 0 ? a.T : 1;
-    {
-        static int sms = 0, skew = 0, rot = 2;
-        if (sms == 0) {
-            if (const char *r = getenv("PT_W45_ROT")) rot = atoi(r);
-            int dev = 0;
-            cudaGetDevice(&dev);
-            int v = 0;
-            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-            const char *env = getenv("PT_W45_SKEW");
-            skew = env ? atoi(env) : 0;
-            sms = v > 0 ? v : 148;
-        }
-        k.num_sms = sms; k.skew_cycles = skew; k.warp_rot = rot;
-    }
+    k.n = n;
     k.out_pos = a.out_pos; k.out_resp = a.out_resp; k.next_guess = a.next_guess;
-    k.traj_pos = a.traj_pos; k.traj_resp = a.traj_resp; k.n = n;
+    k.traj_pos = a.traj_pos; k.traj_resp = a.traj_resp;
     k.dbg = g_dbg;
-    const size_t smem = (size_t)(FR * PIN + 1) * sizeof(float) + (size_t)FR * PM * sizeof(float2);
+    {
+        static int skew = -1;
+        if (skew < 0) { const char *e2 = getenv("PT_W45_SKEW"); skew = e2 ? atoi(e2) : 1; }
+        k.skew = skew;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, vsm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&vsm, cudaDevAttrMultiProcessorCount, dev);
+        sms = vsm > 0 ? vsm : 148;
+    }
+    // one CTA per SM, two windows per CTA; with n ≤ #SMs every window gets its own SM
+    const int grid = std::min(sms, n);
+    const size_t smem = 2 * HALF_SMEM;
     if (pixel == 0) {
         e = cudaFuncSetAttribute(dog_window45_argmax<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        dog_window45_argmax<uint8_t><<<n, THREADS, smem, s>>>(k, tp);
+        dog_window45_argmax<uint8_t><<<grid, CTA_THREADS, smem, s>>>(k, tp);
     } else {
         e = cudaFuncSetAttribute(dog_window45_argmax<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        dog_window45_argmax<float><<<n, THREADS, smem, s>>>(k, tp);
+        dog_window45_argmax<float><<<grid, CTA_THREADS, smem, s>>>(k, tp);
     }
     return cudaGetLastError();
 }
