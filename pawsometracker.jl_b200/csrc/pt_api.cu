@@ -244,7 +244,7 @@ void decompose(pt::WinArgs &a, int nwin)
     const int total = nwin * a.strips;
     int chunks = 1;
     if (total < target) {
-        chunks = (target + total - 1) / total;
+        chunks = std::max(1, target / total);         // never more CTAs than one resident wave (no tail wave)
         const int maxc = (a.wr + pt::kBatchRows - 1) / pt::kBatchRows;
         chunks = std::max(1, std::min(chunks, maxc));
     }

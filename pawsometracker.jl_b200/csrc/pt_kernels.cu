@@ -33,8 +33,87 @@ __device__ __forceinline__ bool key_better(float v, unsigned int idx, float bv, 
     return v > bv || (v == bv && idx < bidx);
 }
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+constexpr int kGenericWarps = kGenericThreads / 32;
+
+// Stage TB footprint rows of one batch: tile column t ↔ frame column X0 + t, tile row rr ↔ frame row
+// Y0 + rr; (pixel − fill) inside the frame, 0 outside (the PaddedView border after the fill shift).
+// Generic path: lanes along the row, one element per lane (coalesced).
 template <typename PixT>
-__global__ void __launch_bounds__(kGenericThreads)
+__device__ __forceinline__ void stage_batch_scalar(const PixT *frame, int pitch, int H, int W, int Y0, int X0, int rows_valid,
+                                                   float fill, float *s_in, int PIN, int warp, int lane)
+{
+    for (int rr = warp; rr < kBatchRows; rr += kGenericWarps) {
+        const int Y = Y0 + rr;
+        const bool yok = (Y >= 0) && (Y < H) && (rr < rows_valid);
+        const PixT *rowp = frame + (size_t)(yok ? Y : 0) * pitch;
+        float *dst = s_in + rr * PIN;
+        for (int t = lane; t < PIN; t += 32) {
+            const int X = X0 + t;
+            dst[t] = (yok && X >= 0 && X < W) ? px_value<PixT>(rowp + X) - fill : 0.f;
+        }
+    }
+}
+
+// u8 frames with 4-byte-aligned rows: one 32-bit load = 4 pixels per lane, bytes outside the frame replaced by
+// the fill byte (→ exactly 0), u8→f32 by the 2^23 trick (PRMT builds 8388608+px, the FADD that subtracts the
+// fill finishes the conversion exactly).  All loads of a thread are issued before the first conversion.
+template <int NWI>   // word iterations per row: ceil(words per row / 32)
+__device__ __forceinline__ void stage_batch_words(const uint8_t *frame, int pitch, int H, int W, int Y0, int X0, int rows_valid,
+                                                  float fill, float *s_in, int PIN, int warp, int lane)
+{
+    constexpr int RPW = kBatchRows / kGenericWarps;    // 8 rows per warp
+    const int xa = X0 & ~3, phase = X0 - xa;
+    const unsigned int fillw = (unsigned int)fill * 0x01010101u;
+    const float cst = 8388608.0f + fill;
+    unsigned int wd[RPW][NWI];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int rr = warp + r * kGenericWarps;
+        const int Y = Y0 + rr;
+        const bool yok = (Y >= 0) && (Y < H) && (rr < rows_valid);
+#pragma unroll
+        for (int i = 0; i < NWI; ++i) {
+            const int wi = lane + 32 * i;
+            const int X = xa + 4 * wi;
+            unsigned int wv = fillw;
+            if (yok && 4 * wi - phase < PIN && X + 3 >= 0 && X < W) {
+                wv = __ldg(reinterpret_cast<const unsigned int *>(frame + (size_t)Y * pitch + X));
+                unsigned int keep = 0u;
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) if (X + bb >= 0 && X + bb < W) keep |= 0xFFu << (8 * bb);
+                wv = (wv & keep) | (fillw & ~keep);
+            }
+            wd[r][i] = wv;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int rr = warp + r * kGenericWarps;
+        float *dst = s_in + rr * PIN;
+#pragma unroll
+        for (int i = 0; i < NWI; ++i) {
+            const int wi = lane + 32 * i;
+            const unsigned int wv = wd[r][i];
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                const int col = 4 * wi - phase + bb;
+                const float val = __uint_as_float(__byte_perm(wv, 0x4B000000u, 0x7540 + bb)) - cst;
+                if (col >= 0 && col < PIN) dst[col] = val;
+            }
+        }
+    }
+}
+
+template <typename PixT>
+__global__ void __launch_bounds__(kGenericThreads, 4)
 dog_rect_argmax_generic(const WinArgs a)
 {
     constexpr int TW = kTileCols, TB = kBatchRows, R = 8, C = kTapChunk;
@@ -42,14 +121,16 @@ dog_rect_argmax_generic(const WinArgs a)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = a.L, w = a.w, Lpad = a.Lpad;
-    const int PIN = (TW + Lpad - 1) | 1;   // odd pitch: lanes walk rows conflict-free
+    const int Lq = ((L + 1 + C - 1) / C) * C;             // column pass walks tap pairs q = 0..L
+    const int PIN = (TW + Lpad - 1) | 1;                  // odd pitch: lanes walk rows conflict-free
     const int RING = L + TB - 1;
-    float2 *s_trow = reinterpret_cast<float2 *>(smem_raw);
-    float2 *s_tcol = s_trow + Lpad;
+    float2 *s_trow = reinterpret_cast<float2 *>(smem_raw);   // [Lpad] (narrow, wide) row taps
+    float2 *s_cpp = s_trow + Lpad;                        // [Lq] (cp[q], cp[q-1])  } column tap pairs: one FFMA2 advances
+    float2 *s_cmq = s_cpp + Lq;                           // [Lq] (cm[q], cm[q-1])  } two vertically adjacent outputs
     constexpr int RP = TW + 1;                            // ring row pitch (float2): odd → row-pass stores conflict-free
-    float2 *s_ring = s_tcol + Lpad;                       // [RING][RP]
+    float2 *s_ring = s_cmq + Lq;                          // [RING][RP]
     float *s_in = reinterpret_cast<float *>(s_ring + (size_t)RING * RP); // [TB][PIN]
-    __shared__ unsigned long long s_best[kGenericThreads / 32];
+    __shared__ unsigned long long s_best[kGenericWarps];
     __shared__ int s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -66,40 +147,60 @@ dog_rect_argmax_generic(const WinArgs a)
     const int nfoot = ch + 2 * w;          // footprint rows of this chunk
     const int nb = (nfoot + TB - 1) / TB;
 
-    for (int k = tid; k < Lpad; k += kGenericThreads) { s_trow[k] = a.taps_row[k]; s_tcol[k] = a.taps_col[k]; }
+    for (int k = tid; k < Lpad; k += kGenericThreads) s_trow[k] = a.taps_row[k];
+    for (int q = tid; q < Lq; q += kGenericThreads) {
+        const float2 cur = (q < L) ? a.taps_col[q] : make_float2(0.f, 0.f);
+        const float2 prv = (q >= 1 && q - 1 < L) ? a.taps_col[q - 1] : make_float2(0.f, 0.f);
+        s_cpp[q] = make_float2(cur.x, prv.x);
+        s_cmq[q] = make_float2(cur.y, prv.y);
+    }
     for (int e = tid; e < RING * RP; e += kGenericThreads) s_ring[e] = make_float2(0.f, 0.f);
 
     const float fill = a.fill[v];
     const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
-    const int valid_cols = TW + 2 * w;     // tile columns that carry real footprint
+    const int X0 = wx0 + c0 - w, Yb = wy0 + r0 - w;
+    const int nwords = (PIN + 3 + 3) / 4;                 // words per staged row incl. phase
+    const bool words_ok = sizeof(PixT) == 1 && ((reinterpret_cast<uintptr_t>(frame) | (uintptr_t)a.pitch) & 3u) == 0 &&
+                          a.pitch >= ((a.W + 3) & ~3) && nwords <= 96;
 
     float best_v = -INFINITY;
     unsigned int best_i = 0xFFFFFFFFu;
 
     for (int b = 0; b < nb; ++b) {
-        // ---- stage TB footprint rows (warp per row, lanes along the row: coalesced)
-        for (int rrow = warp; rrow < TB; rrow += kGenericThreads / 32) {
-            const int f = b * TB + rrow;
-            const int Y = wy0 + r0 - w + f;
-            const bool yok = (Y >= 0) && (Y < a.H) && (f < nfoot);
-            const PixT *rowp = frame + (size_t)(yok ? Y : 0) * a.pitch;
-            float *dst = s_in + rrow * PIN;
-            const int X0 = wx0 + c0 - w;
-            for (int t = lane; t < PIN; t += 32) {
-                const int X = X0 + t;
-                float val = 0.f;
-                if (yok && X >= 0 && X < a.W && t < valid_cols) val = px_value<PixT>(rowp + X) - fill;
-                dst[t] = val;
+        // ---- stage TB footprint rows
+        const int rows_valid = nfoot - b * TB;
+        if (words_ok) {
+            const uint8_t *f8 = reinterpret_cast<const uint8_t *>(frame);
+            if (nwords <= 32) stage_batch_words<1>(f8, a.pitch, a.H, a.W, Yb + b * TB, X0, rows_valid, fill, s_in, PIN, warp, lane);
+            else if (nwords <= 64) stage_batch_words<2>(f8, a.pitch, a.H, a.W, Yb + b * TB, X0, rows_valid, fill, s_in, PIN, warp, lane);
+            else stage_batch_words<3>(f8, a.pitch, a.H, a.W, Yb + b * TB, X0, rows_valid, fill, s_in, PIN, warp, lane);
+        } else {
+            stage_batch_scalar<PixT>(frame, a.pitch, a.H, a.W, Yb + b * TB, X0, rows_valid, fill, s_in, PIN, warp, lane);
+        }
+        // warm L2 with the next batch of rows while this one is filtered
+        if (b + 1 < nb) {
+            const int nl = ((PIN * (int)sizeof(PixT) + 127) >> 7) + 1;
+            const long long rowbytes = (long long)a.W * (int)sizeof(PixT);
+            const long long xb = ((long long)X0 * (int)sizeof(PixT)) & ~127LL;
+            for (int rr = warp; rr < TB; rr += kGenericWarps) {
+                const int Y = Yb + (b + 1) * TB + rr;
+                for (int ln = lane; ln < nl; ln += 32) {
+                    const long long off = xb + ((long long)ln << 7);
+                    if (Y >= 0 && Y < a.H && off >= 0 && off < rowbytes)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(frame + (size_t)Y * a.pitch) + off));
+                }
             }
         }
         __syncthreads();
 
-        // ---- row pass: lane = footprint row of the batch, warp = group of 8 output columns
+        // ---- row pass: lane = footprint row of the batch, warp = group of 8 output columns; one packed
+        // FFMA2 advances (narrow, wide) of an output together
         {
             const float *src = s_in + lane * PIN + warp * R;
-            float ap[R], am[R], win[R + C - 1];
+            float2 acc[R];
+            float win[R + C - 1];
 #pragma unroll
-            for (int j = 0; j < R; ++j) { ap[j] = 0.f; am[j] = 0.f; }
+            for (int j = 0; j < R; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < R - 1; ++j) win[j] = src[j];
 #pragma unroll 1
@@ -110,10 +211,7 @@ dog_rect_argmax_generic(const WinArgs a)
                 for (int t = 0; t < C; ++t) {
                     const float2 g = s_trow[k0 + t];
 #pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        ap[j] = fmaf(win[j + t], g.x, ap[j]);
-                        am[j] = fmaf(win[j + t], g.y, am[j]);
-                    }
+                    for (int j = 0; j < R; ++j) acc[j] = ffma2(make_float2(win[j + t], win[j + t]), g, acc[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < R - 1; ++j) win[j] = win[j + C];
@@ -121,20 +219,22 @@ dog_rect_argmax_generic(const WinArgs a)
             const int f = b * TB + lane;
             float2 *dst = s_ring + (size_t)(f % RING) * RP + warp * R;
 #pragma unroll
-            for (int j = 0; j < R; ++j) dst[j] = make_float2(ap[j], am[j]);
+            for (int j = 0; j < R; ++j) dst[j] = acc[j];
         }
         __syncthreads();
 
-        // ---- column pass: lane = output column, warp = group of 8 output rows
+        // ---- column pass: lane = output column, warp = group of 8 output rows; outputs (2p, 2p+1) share one
+        // packed accumulator: input row 2p+k meets tap k of the even output and tap k-1 of the odd one
         const int o_base = b * TB - 2 * w;   // first output row whose support is now complete
         if (o_base + TB > 0 && o_base < ch) {
             const int f_start = o_base + warp * R;
             int slot = f_start % RING;
             if (slot < 0) slot += RING;
             const float2 *ring_x = s_ring + lane;
-            float acc[R], wp[R + C - 1], wm[R + C - 1];
+            float2 accP[R / 2], accM[R / 2];      // narrow / wide parts: 8 independent dependency chains
+            float wp[R + C - 1], wm[R + C - 1];
 #pragma unroll
-            for (int j = 0; j < R; ++j) acc[j] = 0.f;
+            for (int p = 0; p < R / 2; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
 #pragma unroll
             for (int j = 0; j < R - 1; ++j) {
                 const float2 m = ring_x[(size_t)slot * RP];
@@ -142,7 +242,7 @@ dog_rect_argmax_generic(const WinArgs a)
                 slot = (slot + 1 == RING) ? 0 : slot + 1;
             }
 #pragma unroll 1
-            for (int k0 = 0; k0 < Lpad; k0 += C) {
+            for (int k0 = 0; k0 < Lq; k0 += C) {
 #pragma unroll
                 for (int t = 0; t < C; ++t) {
                     const float2 m = ring_x[(size_t)slot * RP];
@@ -151,12 +251,11 @@ dog_rect_argmax_generic(const WinArgs a)
                 }
 #pragma unroll
                 for (int t = 0; t < C; ++t) {
-                    const float2 g = s_tcol[k0 + t];
+                    const float2 gp = s_cpp[k0 + t], gm = s_cmq[k0 + t];
 #pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        acc[j] = fmaf(wp[j + t], g.x, acc[j]);
-                        acc[j] = fmaf(wm[j + t], g.y, acc[j]);
-                    }
+                    for (int p = 0; p < R / 2; ++p) accP[p] = ffma2(make_float2(wp[2 * p + t], wp[2 * p + t]), gp, accP[p]);
+#pragma unroll
+                    for (int p = 0; p < R / 2; ++p) accM[p] = ffma2(make_float2(wm[2 * p + t], wm[2 * p + t]), gm, accM[p]);
                 }
 #pragma unroll
                 for (int j = 0; j < R - 1; ++j) { wp[j] = wp[j + C]; wm[j] = wm[j + C]; }
@@ -165,7 +264,7 @@ dog_rect_argmax_generic(const WinArgs a)
             for (int j = 0; j < R; ++j) {
                 const int o = f_start + j;
                 if (o >= 0 && o < ch && lane < sw) {
-                    const float val = acc[j] + 0.0f;
+                    const float val = ((j & 1) ? accP[j / 2].y + accM[j / 2].y : accP[j / 2].x + accM[j / 2].x) + 0.0f;
                     const unsigned int idx = (unsigned int)(c0 + lane) * (unsigned int)a.wr + (unsigned int)(r0 + o);
                     if (key_better(val, idx, best_v, best_i)) { best_v = val; best_i = idx; }
                     if (a.map_out)
@@ -188,7 +287,7 @@ dog_rect_argmax_generic(const WinArgs a)
     __syncthreads();
     if (tid == 0) {
         unsigned long long k = s_best[0];
-        for (int i = 1; i < kGenericThreads / 32; ++i) k = s_best[i] > k ? s_best[i] : k;
+        for (int i = 1; i < kGenericWarps; ++i) k = s_best[i] > k ? s_best[i] : k;
         atomicMax(a.keys + v, k);
         __threadfence();
         const unsigned int total = (unsigned int)(a.strips * a.chunks);
@@ -207,7 +306,8 @@ size_t generic_smem_bytes(int L, int Lpad)
 {
     const int PIN = (kTileCols + Lpad - 1) | 1;
     const int RING = L + kBatchRows - 1;
-    return (size_t)2 * Lpad * sizeof(float2) + (size_t)RING * (kTileCols + 1) * sizeof(float2) +
+    const int Lq = ((L + 1 + kTapChunk - 1) / kTapChunk) * kTapChunk;
+    return (size_t)(Lpad + 2 * Lq) * sizeof(float2) + (size_t)RING * (kTileCols + 1) * sizeof(float2) +
            (size_t)kBatchRows * PIN * sizeof(float);
 }
 

@@ -294,32 +294,35 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         if (tid < COL_ITEMS) {
             const int h = tid / WC, xq = tid - h * WC;
             const float2 *col = s_mid + (h * R) * PM + xq;
-            // outputs (2p, 2p+1) share one packed accumulator; output R-1 = 8 stays scalar
-            float2 acc2[R / 2];
-            float acc8 = 0.f;
+            // outputs (2p, 2p+1) share packed accumulators; output R-1 = 8 stays scalar.  Narrow and wide
+            // parts accumulate separately (10 independent dependency chains) and are summed at the end.
+            float2 accP[R / 2], accM[R / 2];
+            float acc8p = 0.f, acc8m = 0.f;
 #pragma unroll
-            for (int p = 0; p < R / 2; ++p) acc2[p] = make_float2(0.f, 0.f);
+            for (int p = 0; p < R / 2; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
 #pragma unroll
             for (int i = 0; i < R + 2 * HW; ++i) {
                 const float2 m = col[i * PM];
 #pragma unroll
                 for (int p = 0; p < R / 2; ++p) {
                     const int q = i - 2 * p;                 // tap of the even output; the odd one uses q-1
-                    if (q >= 0 && q <= L) {
-                        acc2[p] = ffma2(make_float2(m.x, m.x), tp.cpp[q], acc2[p]);
-                        acc2[p] = ffma2(make_float2(m.y, m.y), tp.cmq[q], acc2[p]);
-                    }
+                    if (q >= 0 && q <= L) accP[p] = ffma2(make_float2(m.x, m.x), tp.cpp[q], accP[p]);
+                }
+#pragma unroll
+                for (int p = 0; p < R / 2; ++p) {
+                    const int q = i - 2 * p;
+                    if (q >= 0 && q <= L) accM[p] = ffma2(make_float2(m.y, m.y), tp.cmq[q], accM[p]);
                 }
                 const int q8 = i - (R - 1);
                 if (q8 >= 0 && q8 < L) {
-                    acc8 = fmaf(m.x, tp.cpp[q8].x, acc8);
-                    acc8 = fmaf(m.y, tp.cmq[q8].x, acc8);
+                    acc8p = fmaf(m.x, tp.cpp[q8].x, acc8p);
+                    acc8m = fmaf(m.y, tp.cmq[q8].x, acc8m);
                 }
             }
             float acc[R];
 #pragma unroll
-            for (int p = 0; p < R / 2; ++p) { acc[2 * p] = acc2[p].x; acc[2 * p + 1] = acc2[p].y; }
-            acc[R - 1] = acc8;
+            for (int p = 0; p < R / 2; ++p) { acc[2 * p] = accP[p].x + accM[p].x; acc[2 * p + 1] = accP[p].y + accM[p].y; }
+            acc[R - 1] = acc8p + acc8m;
             float bv = acc[0] + 0.0f;
             int bj = 0;
 #pragma unroll

@@ -438,6 +438,86 @@ def test_large_batch_1080p_properties(gpu_pkg):
     assert np.all(resp > 0.08)
 
 
+@pytest.mark.parametrize("n,T", [(1, 1), (3, 5), (149, 4), (300, 3), (700, 2)])
+def test_batch_sizes_exercise_cta_video_loop(gpu_pkg, oracle, n, T):
+    """dog_window45_argmax hosts two videos per CTA and loops `v += 2·#CTAs`: cover one video, an odd
+    count just above the SM count (lone second halves), and more videos than one wave holds.  Every
+    video has its own frame content; spot-check a sample of videos against the oracle loop, all of them
+    against ground truth, and the per-step path against the chained one."""
+    import torch
+    H, W = 128, 160
+    rng = np.random.default_rng(n * 31 + T)
+    c0 = np.stack([rng.integers(20, H - 20, n), rng.integers(20, W - 20, n)], axis=-1)
+    cent = np.stack([c0 + rng.integers(-7, 8, (n, 2)) * (t > 0) for t in range(T)])      # (T, n, 2), 1-based
+    cent = np.clip(np.cumsum(np.concatenate([c0[None], np.diff(cent, axis=0)]), axis=0), 1, [H, W])
+    frames = np.full((T, n, H, W), 128, np.uint8)
+    yy, xx = np.ogrid[0:H, 0:W]
+    for t in range(T):
+        for v in range(n):
+            cy, cx = cent[t, v] - 1
+            y0, y1, x0, x1 = max(0, cy - 12), min(H, cy + 13), max(0, cx - 12), min(W, cx + 13)
+            sub = frames[t, v, y0:y1, x0:x1]
+            sub[(yy[y0:y1] - cy) ** 2 + (xx[:, x0:x1] - cx) ** 2 <= 144] = 0
+    dev = torch.from_numpy(frames).cuda()
+    start = cent[0] + rng.integers(-4, 5, (n, 2))
+    with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
+        assert b.kernel_name == "dog_window45_argmax"
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        b.set_fill(128)
+        b.set_guess(start)
+        ij, resp = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        b.set_guess(start)
+        per_step = []
+        for t in range(T):
+            b.bind_device_frames(dev.data_ptr() + t * n * H * W, H * W, W)
+            o, _ = b.step(None)
+            per_step.append(o.copy())
+    np.testing.assert_array_equal(ij, np.stack(per_step))
+    for v in sorted(set([0, n - 1, n // 2] + list(rng.integers(0, n, 4)))):
+        ref, near = oracle_track(oracle, [frames[t, v] for t in range(T)], 25, True, (45, 45), tuple(start[v]))
+        assert near == 0
+        np.testing.assert_array_equal(ij[:, v], ref)
+    # disks that are fully inside the frame are found exactly at their centre
+    inside = (cent[..., 0] > 13) & (cent[..., 0] < H - 13) & (cent[..., 1] > 13) & (cent[..., 1] < W - 13)
+    np.testing.assert_array_equal(ij[inside], cent[inside])
+
+
+def test_float32_frames_chained_and_batched(gpu_pkg, oracle):
+    """f32 frames through the chained (resident) path of the specialised kernel."""
+    import torch
+    n, T, H, W = 5, 6, 150, 170
+    vids = [gpu_pkg.make_video(H=H, W=W, target_width=25, start_ij=(75, 85), seconds=10.0, fps=24.0, seed=40 + s)
+            for s in range(n)]
+    f8 = np.stack([np.stack([v.frame(t) for v in vids]) for t in range(T)])
+    f32 = f8.astype(np.float32) / np.float32(255.0)
+    dev = torch.from_numpy(f32).cuda()
+    with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True, dtype=np.float32) as b:
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        assert (b.compute_fill() == 128).all()
+        b.set_guess(np.tile([75, 85], (n, 1)))
+        ij, resp = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+    for v in range(n):
+        ref, near = oracle_track(oracle, [f8[t, v] for t in range(T)], 25, True, (45, 45), (75, 85))
+        assert near == 0
+        np.testing.assert_array_equal(ij[:, v], ref)
+
+
+def test_guess_far_outside_frame(gpu_pkg, oracle):
+    """A guess outside the frame is legal (the window then sees mostly the fill border); the result is clamped."""
+    f = disk_frame(100, 120, 10, 110, 12)
+    for guess in [(-30, 150), (1, 120), (140, -20), (30, 130)]:
+        trk = gpu_pkg.Tracker(f, 25, (45, 45), True)
+        try:
+            ref = oracle.step(f, 128, 25, True, (45, 45), guess)
+            got = trk(guess)
+            assert 1 <= got[0] <= 100 and 1 <= got[1] <= 120
+            if not ref.near_tie(RTOL):
+                assert got == (ref.i, ref.j)
+                assert abs(trk.last_response - ref.resp) <= RTOL * ref.maxabs
+        finally:
+            trk.close()
+
+
 def test_error_behaviour(gpu_pkg):
     f = np.full((64, 64), 128, np.uint8)
     b = gpu_pkg.TrackerBatch(2, (64, 64), 10, (21, 21), True)
