@@ -75,7 +75,7 @@ struct Args45 {
     int4 *out_pos; float *out_resp;     // [n] last step
     int2 *next_guess;                   // [n] or null
     int4 *traj_pos; float *traj_resp;   // [T][n] or null
-    int skew;                           // 1: half 1 of each CTA starts half a frame late (anti-phase)
+    int skew;                           // 1: alternate the row passes of the two windows of a CTA (token)
     long long *dbg;                     // optional [n][T][6]: smid|globaltimer, clock64 at start / stage / row / col / end
 };
 
@@ -138,17 +138,20 @@ __device__ __forceinline__ void stage_tile<float>(const float *frame, int pitch,
 // exact.  Each lane rotates its word by lane/8 bytes so the four stores of a warp hit 32
 // distinct banks.  Requires frame base, pitch and strides to be multiples of 4 bytes and
 // pitch ≥ round_up(W, 4) (checked by window45_supported).
-template <>
-__device__ __forceinline__ void stage_tile<uint8_t>(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
-                                                    float fill, float *s_in, int warp, int lane)
+template <bool kInterior>
+__device__ __forceinline__ void stage_tile_u8(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
+                                              float fill, float *s_in, int warp, int lane)
 {
     constexpr int RPW = (FR + NWARPS - 1) / NWARPS;
     const int xa = fx0 & ~3, phase = fx0 - xa;             // aligned start, phase 0..3
     const int X = xa + 4 * lane;                            // frame column of this lane's word
     const unsigned int fillw = (unsigned int)fill * 0x01010101u;
-    unsigned int keep = 0u;                                 // bytes of the word inside [0, W)
+    unsigned int keep = 0xFFFFFFFFu;                        // bytes of the word inside [0, W)
+    if (!kInterior) {
+        keep = 0u;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < W) keep |= 0xFFu << (8 * b);
+        for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < W) keep |= 0xFFu << (8 * b);
+    }
     const bool wordok = keep != 0u && (4 * lane - phase < FC);
     const int rot = lane >> 3;
     int col[4];
@@ -159,20 +162,21 @@ __device__ __forceinline__ void stage_tile<uint8_t>(const uint8_t *frame, int pi
         cok[k] = col[k] >= 0 && col[k] < FC;
     }
     unsigned int wd[RPW];
+    const uint8_t *base = frame + (size_t)(fy0 + warp) * pitch + X;      // only dereferenced when valid
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
         const int Y = fy0 + f;
-        const bool ok = wordok && (f < FR) && (Y >= 0) && (Y < H);
+        const bool ok = wordok && (f < FR) && (kInterior || ((Y >= 0) && (Y < H)));
         wd[r] = fillw;
-        if (ok) wd[r] = __ldg(reinterpret_cast<const unsigned int *>(frame + (size_t)Y * pitch + X));
+        if (ok) wd[r] = __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)(r * NWARPS) * pitch));
     }
     const float cst = 8388608.0f + fill;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
         if (f < FR) {
-            unsigned int w = (wd[r] & keep) | (fillw & ~keep);
+            unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
             w = __funnelshift_r(w, w, 8 * rot);            // byte k of w = pixel (k + rot) & 3 of the word
             float *dst = s_in + f * PIN;
 #pragma unroll
@@ -182,6 +186,16 @@ __device__ __forceinline__ void stage_tile<uint8_t>(const uint8_t *frame, int pi
             }
         }
     }
+}
+
+template <>
+__device__ __forceinline__ void stage_tile<uint8_t>(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
+                                                    float fill, float *s_in, int warp, int lane)
+{
+    // interior: every aligned word the footprint touches lies inside the frame → no byte masks, no row checks
+    const bool interior = (fy0 >= 0) && (fy0 + FR <= H) && ((fx0 & ~3) >= 0) && ((fx0 & ~3) + 4 * 28 <= W);
+    if (interior) stage_tile_u8<true>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    else stage_tile_u8<false>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
 }
 
 } // namespace
@@ -210,13 +224,18 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
     unsigned long long *s_key = s_keys[half];
     const int stride = 2 * (int)gridDim.x;
 
-    // Anti-phase start: both halves do identical work per frame, so started together they stay in
-    // lockstep — colliding on the FMA pipes in the row/column passes and leaving them idle while
-    // both stage.  Half 1 therefore starts when half 0 has finished its first row pass (about half
-    // a frame later); equal periods keep the offset.
-    const bool skewed = a.skew && ((int)blockIdx.x + (int)gridDim.x < a.n);
-    if (skewed && half == 1) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory");
-    bool released = !(skewed && half == 0);
+    // Staggering the two windows: left alone the halves drift into lockstep (measured) — both stage at
+    // once, leaving the FMA pipes idle, then both run their passes at once.  The row passes are therefore
+    // strictly alternated with a token (named barriers 3 and 4 used as semaphores: the 256 threads of one
+    // half arrive, the 256 of the other wait): A.row(r) → B.row(r) → A.row(r+1) → …  Each window's
+    // stage / reduce / column pass then overlaps the other window's row pass.  NA / NB = number of row
+    // passes each half will run in this launch, so the alternation stops cleanly when one half is done.
+    const int cntA = ((int)blockIdx.x < a.n) ? (a.n - 1 - (int)blockIdx.x) / stride + 1 : 0;
+    const int firstB = (int)blockIdx.x + (int)gridDim.x;
+    const int cntB = (firstB < a.n) ? (a.n - 1 - firstB) / stride + 1 : 0;
+    const int NA = cntA * a.T, NB = cntB * a.T;
+    const bool tokens = a.skew != 0 && NB > 0;
+    int round = 0;
 
   for (int v = (int)blockIdx.x + (int)gridDim.x * half; v < a.n; v += stride) {
     const float fill = a.fill[v];
@@ -261,6 +280,10 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         }
         bar_half(half);
         if (dbg && tid == 0) dbg[2] = clock64();
+        if (tokens) {                                          // wait for the row-pass token
+            if (half == 0) { if (round >= 1 && round - 1 < NB) asm volatile("bar.sync 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
+            else           { if (round < NA) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
+        }
 
         // ---- row pass: item = (footprint row f, column group gq); lanes walk rows
 #pragma unroll 1
@@ -286,7 +309,11 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             for (int j = 0; j < RR; ++j) dst[j] = acc[j];
         }
         bar_half(half);
-        if (!released) { asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); released = true; }
+        if (tokens) {                                          // hand the row-pass token to the other window
+            if (half == 0) { if (round < NB) asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
+            else           { if (round + 1 < NA) asm volatile("bar.arrive 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
+        }
+        ++round;
         if (dbg && tid == 0) dbg[3] = clock64();
 
         // ---- column pass + running argmax: item = (column xq, row group h); lanes walk columns

@@ -67,3 +67,18 @@ for label in ("cold (L2 flushed)", "warm (same slots again)", "cold again"):
         q = np.percentile(per_cta[m], [0, 25, 50, 75, 100])
         print(f"   windows on SMs hosting {k}: {m.sum():3d}; mean frame period min/25/50/75/max = " + "/".join(f"{x:.0f}" for x in q)
               + " | " + " ".join(f"{nm} {ph[m][:, 2:, i].mean():.0f}" for i, nm in enumerate(names)))
+
+# ---- timeline of one SM that hosts two windows (last measured run)
+try:
+    sm0 = smid[:, 0]
+    cnt = np.bincount(sm0, minlength=148)
+    target_sm = int(np.flatnonzero(cnt == 2)[0])
+    vs = np.flatnonzero(sm0 == target_sm)
+    base = d[vs][:, :, 1].min()
+    print(f"timeline on SM {target_sm}, videos {vs.tolist()} (cycles since first start; S=stage R=row C=col X=reduce):")
+    for t in range(6, 10):
+        for v in vs:
+            st = d[v, t, 1:6] - base
+            print(f"  v{v} t{t}: S {st[0]:7d}-{st[1]:7d} R -{st[2]:7d} C -{st[3]:7d} X -{st[4]:7d}")
+except Exception as e:
+    print("timeline failed:", e)
