@@ -171,6 +171,7 @@ struct pt_batch {
     std::vector<float> h_taps;           // host copy: row narrow | row wide | col narrow | col wide, each L
     int2 *d_guess = nullptr;
     bool guess_set = false;
+    bool staging_busy = false;           // an async H2D from the guess staging may be in flight
     int2 *d_center = nullptr;            // crop-mode guess: centre of the footprint
     unsigned long long *d_keys = nullptr;
     unsigned int *d_counters = nullptr;
@@ -252,12 +253,25 @@ void decompose(pt::WinArgs &a, int nwin)
     a.chunks = (a.wr + a.CH - 1) / a.CH;
 }
 
+// Kernel choice shared by every path (so host-footprint, resident and per-step calls round identically).
+// Thread-safe: touches no batch state.
+cudaError_t launch_windows(const pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
+{
+    if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
+        return pt::launch_window45(a, nwin, b->pixel, s);
+    if (b->use45 && pt::rect45_supported(a, b->pixel))
+        return pt::launch_rect45(a, nwin, b->pixel, s);
+    decompose(a, nwin);
+    return pt::launch_generic(a, nwin, b->pixel, s);
+}
+
 int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
 {
     cudaError_t e;
     bool done = false;
-    if (b->use45 && !a.rect_mode && !a.map_out) {
-        // preferred: 4 CTAs per window (needs all 4n CTAs co-resident and u8 frames)
+    static const bool quad_enabled = getenv("PT_ENABLE_QUAD") != nullptr;
+    if (quad_enabled && b->use45 && !a.rect_mode && !a.map_out) {
+        // experimental: 4 CTAs per window (needs all 4n CTAs co-resident and u8 frames)
         const size_t slots = (size_t)nwin * (size_t)(a.T > 0 ? a.T : 1);
         int rc = b->d_xkeys.ensure(slots * sizeof(unsigned long long)); if (rc) return rc;
         rc = b->d_xcnt.ensure(slots * sizeof(unsigned int)); if (rc) return rc;
@@ -267,15 +281,9 @@ int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
             CU(cudaMemsetAsync(a.xcnt, 0, slots * sizeof(unsigned int), s));
             e = pt::launch_window45_quad(a, nwin, s);
             done = true;
-        } else if (pt::window45_supported(a, b->pixel)) {
-            e = pt::launch_window45(a, nwin, b->pixel, s);
-            done = true;
         }
     }
-    if (!done) {
-        decompose(a, nwin);
-        e = pt::launch_generic(a, nwin, b->pixel, s);
-    }
+    if (!done) e = launch_windows(b, a, nwin, s);
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     b->launches += 1;
     return PT_OK;
@@ -294,10 +302,11 @@ int upload_guess(pt_batch *b, const int32_t *g, cudaStream_t s)
     if (rc) return rc;
     // staging region [n*16, n*24) of h_out is reserved for guesses
     int32_t *st = reinterpret_cast<int32_t *>((char *)b->h_out.p + (size_t)b->n * 24);
-    CU(cudaStreamSynchronize(s)); // an earlier async copy may still be reading the staging
+    if (b->staging_busy) { CU(cudaStreamSynchronize(s)); b->staging_busy = false; }   // earlier async copy still reading it?
     memcpy(st, g, sizeof(int32_t) * 2 * (size_t)b->n);
     CU(cudaMemcpyAsync(b->d_guess, st, sizeof(int2) * (size_t)b->n, cudaMemcpyHostToDevice, s));
     b->guess_set = true;
+    b->staging_busy = true;
     return PT_OK;
 }
 
@@ -353,6 +362,7 @@ int read_results(pt_batch *b, int32_t *out_ij, int32_t *out_raw, float *out_resp
     CU(cudaMemcpyAsync(hp, b->d_pos, n * 16, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(hr, b->d_resp, n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    b->staging_busy = false;
     for (size_t v = 0; v < n; ++v) {
         if (out_ij) { out_ij[2 * v] = hp[v].x; out_ij[2 * v + 1] = hp[v].y; }
         if (out_raw) { out_raw[2 * v] = hp[v].z; out_raw[2 * v + 1] = hp[v].w; }
@@ -727,10 +737,7 @@ void lane_worker(HostTrack *ht, pt_lane *ln)
             a.fill = b->d_fill + ln->v0;
             a.keys = b->d_keys + ln->v0; a.counters = b->d_counters + ln->v0;
             a.out_pos = b->d_pos + ln->v0; a.out_resp = b->d_resp + ln->v0;
-            cudaError_t le;
-            if (b->use45 && pt::window45_supported(a, b->pixel)) le = pt::launch_window45(a, nl, b->pixel, ln->stream);
-            else { decompose(a, nl); le = pt::launch_generic(a, nl, b->pixel, ln->stream); }
-            e = le;
+            e = launch_windows(b, a, nl, ln->stream);
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(hres, b->d_pos + ln->v0, sizeof(int4) * nl, cudaMemcpyDeviceToHost, ln->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(hresp, b->d_resp + ln->v0, sizeof(float) * nl, cudaMemcpyDeviceToHost, ln->stream);
@@ -934,10 +941,14 @@ int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int wc,
     a.fill = b->d_fill + v; a.keys = b->d_keys + v; a.counters = b->d_counters + v;
     a.out_pos = b->d_pos + v; a.out_resp = b->d_resp + v;
     rc = launch_step(b, a, 1, b->stream); if (rc) return rc;
-    int4 p; float r;
-    CU(cudaMemcpyAsync(&p, b->d_pos + v, sizeof p, cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaMemcpyAsync(&r, b->d_resp + v, sizeof r, cudaMemcpyDeviceToHost, b->stream));
+    rc = b->h_out.ensure((size_t)b->n * 32); if (rc) return rc;
+    int4 *hp = reinterpret_cast<int4 *>(b->h_out.p);                 // pinned: truly asynchronous copies
+    float *hr = reinterpret_cast<float *>((char *)b->h_out.p + 16);
+    CU(cudaMemcpyAsync(hp, b->d_pos + v, sizeof(int4), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(hr, b->d_resp + v, sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
+    b->staging_busy = false;
+    const int4 p = *hp; const float r = *hr;
     if (oi) *oi = p.x; if (oj) *oj = p.y; if (raw_i) *raw_i = p.z; if (raw_j) *raw_j = p.w; if (resp) *resp = r;
     return PT_OK;
 }
@@ -954,6 +965,7 @@ const char *pt_batch_kernel_name(const pt_batch *b)
         b->n <= pt::window45_quad_max_windows())
         return pt::window45_quad_name();
     if (b->use45 && pt::window45_supported(a, b->pixel)) return pt::window45_name();
+    if (b->use45 && a.L == 65 && !getenv("PT_DISABLE_RECT45") && (long long)a.wr * a.wc >= 24 * 24) return pt::rect45_name();
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
 }
 

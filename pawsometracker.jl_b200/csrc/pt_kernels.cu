@@ -317,12 +317,10 @@ cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s)
     dim3 grid((unsigned)a.strips, (unsigned)a.chunks, (unsigned)n);
     cudaError_t e;
     if (pixel == 0) {
-        e = cudaFuncSetAttribute(dog_rect_argmax_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect_argmax_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
         dog_rect_argmax_generic<uint8_t><<<grid, kGenericThreads, smem, s>>>(a);
     } else {
-        e = cudaFuncSetAttribute(dog_rect_argmax_generic<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect_argmax_generic<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
         dog_rect_argmax_generic<float><<<grid, kGenericThreads, smem, s>>>(a);
     }
     return cudaGetLastError();

@@ -96,6 +96,11 @@ const char *window45_name();
 void window45_set_debug(long long *dev_buf);
 long long *window45_debug_ptr();   // phase-timestamp buffer [n][T][6] (profiling aid), nullptr = off
 
+// l = 65 rectangles of any size cut into 45x45 tiles evaluated like windows (auto-detect, full frame, …).
+bool rect45_supported(const WinArgs &a, int pixel);
+cudaError_t launch_rect45(const WinArgs &a, int n, int pixel, cudaStream_t s);
+const char *rect45_name();
+
 // Second-generation specialised kernel: 4 CTAs per window, u8 frames, cooperative launch.
 bool window45_quad_supported(const WinArgs &a, int n, int pixel);
 int window45_quad_max_windows();

@@ -200,6 +200,90 @@ __device__ __forceinline__ void stage_tile<uint8_t>(const uint8_t *frame, int pi
 
 } // namespace
 
+
+// ---- row pass over one staged 109×109 tile: item = (footprint row f, group gq of 5 output columns);
+// lanes walk rows.  One FADD (symmetric fold) feeds one packed FFMA2 advancing (narrow, wide).
+__device__ __forceinline__ void row_pass45(const float *s_in, float2 *s_mid, int tid, const Taps45 &tp)
+{
+#pragma unroll 1
+    for (int item = tid; item < ROW_ITEMS; item += THREADS) {
+        const int gq = item / FR, f = item - gq * FR;
+        const float *row = s_in + f * PIN + gq * RR;
+        float x[RR + 2 * HW];
+#pragma unroll
+        for (int i = 0; i < RR + 2 * HW; ++i) x[i] = row[i];
+        float2 acc[RR];                                  // (narrow, wide) per output
+#pragma unroll
+        for (int j = 0; j < RR; ++j) acc[j] = fmul2(make_float2(x[j + HW], x[j + HW]), tp.rt[0]);
+#pragma unroll
+        for (int d = 1; d <= HW; ++d) {
+#pragma unroll
+            for (int j = 0; j < RR; ++j) {
+                const float s = x[j + HW - d] + x[j + HW + d];   // exact for u8 frames (integers)
+                acc[j] = ffma2(make_float2(s, s), tp.rt[d], acc[j]);
+            }
+        }
+        float2 *dst = s_mid + f * PM + gq * RR;
+#pragma unroll
+        for (int j = 0; j < RR; ++j) dst[j] = acc[j];
+    }
+}
+
+// ---- column pass + per-thread argmax over the 45×45 outputs of a tile: item = (column xq, row group h);
+// lanes walk columns.  Outputs (2p, 2p+1) share packed accumulators; output 8 stays scalar; narrow and wide
+// parts accumulate separately (10 independent dependency chains).  The tile sits at (gy0, gx0) inside an
+// output rectangle of wr_tot × wc_tot: outputs beyond it are masked, the key carries the rectangle's
+// column-major index.  map_out (optional) receives the responses, row-major with pitch wc_tot.
+__device__ __forceinline__ unsigned long long col_pass45(const float2 *s_mid, int tid, const Taps45 &tp,
+                                                         int gy0, int gx0, int wr_tot, int wc_tot, float *map_out)
+{
+    if (tid >= COL_ITEMS) return 0ull;
+    const int h = tid / WC, xq = tid - h * WC;
+    const float2 *col = s_mid + (h * R) * PM + xq;
+    float2 accP[R / 2], accM[R / 2];
+    float acc8p = 0.f, acc8m = 0.f;
+#pragma unroll
+    for (int p = 0; p < R / 2; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int i = 0; i < R + 2 * HW; ++i) {
+        const float2 m = col[i * PM];
+#pragma unroll
+        for (int p = 0; p < R / 2; ++p) {
+            const int q = i - 2 * p;                 // tap of the even output; the odd one uses q-1
+            if (q >= 0 && q <= L) accP[p] = ffma2(make_float2(m.x, m.x), tp.cpp[q], accP[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < R / 2; ++p) {
+            const int q = i - 2 * p;
+            if (q >= 0 && q <= L) accM[p] = ffma2(make_float2(m.y, m.y), tp.cmq[q], accM[p]);
+        }
+        const int q8 = i - (R - 1);
+        if (q8 >= 0 && q8 < L) {
+            acc8p = fmaf(m.x, tp.cpp[q8].x, acc8p);
+            acc8m = fmaf(m.y, tp.cmq[q8].x, acc8m);
+        }
+    }
+    float acc[R];
+#pragma unroll
+    for (int p = 0; p < R / 2; ++p) { acc[2 * p] = accP[p].x + accM[p].x; acc[2 * p + 1] = accP[p].y + accM[p].y; }
+    acc[R - 1] = acc8p + acc8m;
+    const int gx = gx0 + xq, gyb = gy0 + h * R;
+    if (gx >= wc_tot || gyb >= wr_tot) return 0ull;
+    float bv = acc[0] + 0.0f;
+    int bj = 0;
+#pragma unroll
+    for (int j = 1; j < R; ++j) {
+        const float val = acc[j] + 0.0f;
+        if (gyb + j < wr_tot && val > bv) { bv = val; bj = j; }   // strict: first maximum within the column segment
+    }
+    if (map_out) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (gyb + j < wr_tot) map_out[(size_t)(gyb + j) * wc_tot + gx] = acc[j] + 0.0f;
+    }
+    return pack_key(bv, (unsigned int)(gx * wr_tot + gyb + bj));
+}
+
 __device__ __forceinline__ void bar_half(int half)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(THREADS) : "memory");
@@ -285,29 +369,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             else           { if (round < NA) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
         }
 
-        // ---- row pass: item = (footprint row f, column group gq); lanes walk rows
-#pragma unroll 1
-        for (int item = tid; item < ROW_ITEMS; item += THREADS) {
-            const int gq = item / FR, f = item - gq * FR;
-            const float *row = s_in + f * PIN + gq * RR;
-            float x[RR + 2 * HW];
-#pragma unroll
-            for (int i = 0; i < RR + 2 * HW; ++i) x[i] = row[i];
-            float2 acc[RR];                                  // (narrow, wide) per output
-#pragma unroll
-            for (int j = 0; j < RR; ++j) acc[j] = fmul2(make_float2(x[j + HW], x[j + HW]), tp.rt[0]);
-#pragma unroll
-            for (int d = 1; d <= HW; ++d) {
-#pragma unroll
-                for (int j = 0; j < RR; ++j) {
-                    const float s = x[j + HW - d] + x[j + HW + d];   // exact for u8 frames (integers)
-                    acc[j] = ffma2(make_float2(s, s), tp.rt[d], acc[j]);
-                }
-            }
-            float2 *dst = s_mid + f * PM + gq * RR;
-#pragma unroll
-            for (int j = 0; j < RR; ++j) dst[j] = acc[j];
-        }
+        row_pass45(s_in, s_mid, tid, tp);
         bar_half(half);
         if (tokens) {                                          // hand the row-pass token to the other window
             if (half == 0) { if (round < NB) asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
@@ -316,49 +378,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         ++round;
         if (dbg && tid == 0) dbg[3] = clock64();
 
-        // ---- column pass + running argmax: item = (column xq, row group h); lanes walk columns
-        unsigned long long key = 0ull;
-        if (tid < COL_ITEMS) {
-            const int h = tid / WC, xq = tid - h * WC;
-            const float2 *col = s_mid + (h * R) * PM + xq;
-            // outputs (2p, 2p+1) share packed accumulators; output R-1 = 8 stays scalar.  Narrow and wide
-            // parts accumulate separately (10 independent dependency chains) and are summed at the end.
-            float2 accP[R / 2], accM[R / 2];
-            float acc8p = 0.f, acc8m = 0.f;
-#pragma unroll
-            for (int p = 0; p < R / 2; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
-#pragma unroll
-            for (int i = 0; i < R + 2 * HW; ++i) {
-                const float2 m = col[i * PM];
-#pragma unroll
-                for (int p = 0; p < R / 2; ++p) {
-                    const int q = i - 2 * p;                 // tap of the even output; the odd one uses q-1
-                    if (q >= 0 && q <= L) accP[p] = ffma2(make_float2(m.x, m.x), tp.cpp[q], accP[p]);
-                }
-#pragma unroll
-                for (int p = 0; p < R / 2; ++p) {
-                    const int q = i - 2 * p;
-                    if (q >= 0 && q <= L) accM[p] = ffma2(make_float2(m.y, m.y), tp.cmq[q], accM[p]);
-                }
-                const int q8 = i - (R - 1);
-                if (q8 >= 0 && q8 < L) {
-                    acc8p = fmaf(m.x, tp.cpp[q8].x, acc8p);
-                    acc8m = fmaf(m.y, tp.cmq[q8].x, acc8m);
-                }
-            }
-            float acc[R];
-#pragma unroll
-            for (int p = 0; p < R / 2; ++p) { acc[2 * p] = accP[p].x + accM[p].x; acc[2 * p + 1] = accP[p].y + accM[p].y; }
-            acc[R - 1] = acc8p + acc8m;
-            float bv = acc[0] + 0.0f;
-            int bj = 0;
-#pragma unroll
-            for (int j = 1; j < R; ++j) {
-                const float val = acc[j] + 0.0f;
-                if (val > bv) { bv = val; bj = j; }       // strict: first maximum within the column segment
-            }
-            key = pack_key(bv, (unsigned int)(xq * WR + h * R + bj));
-        }
+        unsigned long long key = col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
@@ -393,6 +413,101 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
     }
     bar_half(half);    // s_key / smem of this half are reused by the next video
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Large rectangles at l = 65 (auto-detect window size .÷ 4, src/PawsomeTracker.jl:99-105; the full-frame
+// DoG benchmark shape; any non-default window_size at target_width 25): the output rectangle is cut into
+// 45×45 tiles and every tile is evaluated exactly like a window by one half-CTA (same staging, row pass,
+// column pass).  Tiles of a rectangle combine through one 64-bit atomicMax per (window, tile) and the
+// last tile decodes, clamps and publishes — the merge of the generic kernel.  Items = (window, tile);
+// half h of CTA c walks items c + S·h, c + S·(h+2), …; the row passes of the two halves alternate by token.
+// ---------------------------------------------------------------------------------------------------
+template <typename PixT>
+__global__ void __launch_bounds__(CTA_THREADS, 1)
+dog_rect45_tiles(const __grid_constant__ WinArgs a, const __grid_constant__ Taps45 tp, int n, int nty, int ntx)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long s_keys[2][2 * NWARPS];
+
+    const int pw = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = (pw >> 2) & 1;
+    const int warp = (((pw & 3) + 2 * half) & 3) + 4 * (pw >> 3);
+    const int tid = warp * 32 + lane;
+    float *s_in = reinterpret_cast<float *>(smem_raw + half * HALF_SMEM);
+    float2 *s_mid = reinterpret_cast<float2 *>(s_in + FR * PIN + 1);
+    unsigned long long *s_key = s_keys[half];
+    const int stride = 2 * (int)gridDim.x;
+    const int tiles = nty * ntx;
+    const long long items = (long long)n * tiles;
+
+    const int firstA = (int)blockIdx.x, firstB = (int)blockIdx.x + (int)gridDim.x;
+    const int NA = (firstA < items) ? (int)((items - 1 - firstA) / stride) + 1 : 0;
+    const int NB = (firstB < items) ? (int)((items - 1 - firstB) / stride) + 1 : 0;
+    const bool tokens = NB > 0;
+    int round = 0;
+
+    for (long long item = (half ? firstB : firstA); item < items; item += stride, ++round) {
+        const int v = (int)(item / tiles), tl = (int)(item - (long long)v * tiles);
+        const int ty = tl / ntx, tx = tl - ty * ntx;
+        int wy0, wx0;
+        if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
+        else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
+        const int gy0 = ty * WR, gx0 = tx * WC;
+        const float fill = a.fill[v];
+        const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
+
+        stage_tile<PixT>(frame, a.pitch, a.H, a.W, wy0 + gy0 - HW, wx0 + gx0 - HW, fill, s_in, warp, lane);
+        bar_half(half);
+        if (tokens) {
+            if (half == 0) { if (round >= 1 && round - 1 < NB) asm volatile("bar.sync 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
+            else           { if (round < NA) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
+        }
+        row_pass45(s_in, s_mid, tid, tp);
+        bar_half(half);
+        if (tokens) {
+            if (half == 0) { if (round < NB) asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
+            else           { if (round + 1 < NA) asm volatile("bar.arrive 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
+        }
+        float *map = a.map_out ? a.map_out + (size_t)v * a.wr * a.wc : nullptr;
+        unsigned long long key = col_pass45(s_mid, tid, tp, gy0, gx0, a.wr, a.wc, map);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+            key = o > key ? o : key;
+        }
+        if (lane == 0) s_key[(round & 1) * NWARPS + warp] = key;
+        bar_half(half);
+        if (tid == 0) {
+            const unsigned long long *kk = s_key + (round & 1) * NWARPS;
+            unsigned long long k = kk[0];
+#pragma unroll
+            for (int i = 1; i < NWARPS; ++i) k = kk[i] > k ? kk[i] : k;
+            atomicMax(a.keys + v, k);
+            __threadfence();
+            const unsigned int prev = atomicAdd(a.counters + v, 1u);
+            if (prev == (unsigned int)tiles - 1u) {
+                __threadfence();
+                const unsigned long long win = atomicExch(a.keys + v, 0ull);
+                a.counters[v] = 0u;
+                publish_result(a, v, win, wy0, wx0);
+            }
+        }
+    }
+}
+
+const char *rect45_name() { return "dog_rect45_tiles"; }
+
+bool rect45_supported(const WinArgs &a, int pixel)
+{
+    if (a.L != L || getenv("PT_DISABLE_RECT45")) return false;
+    if ((long long)a.wr * a.wc < 24 * 24) return false;     // tiny windows: the generic strip kernel wastes less
+    if (pixel == 0) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(a.frames) | (uintptr_t)a.pitch | (uintptr_t)a.frame_stride) & 3u) == 0;
+        if (!aligned || a.pitch < ((a.W + 3) & ~3)) return false;
+    }
+    return true;
 }
 
 const char *window45_name() { return "dog_window45_argmax"; }
@@ -458,13 +573,39 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
     const int grid = std::min(sms, n);
     const size_t smem = 2 * HALF_SMEM;
     if (pixel == 0) {
-        e = cudaFuncSetAttribute(dog_window45_argmax<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_argmax<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
         dog_window45_argmax<uint8_t><<<grid, CTA_THREADS, smem, s>>>(k, tp);
     } else {
-        e = cudaFuncSetAttribute(dog_window45_argmax<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_argmax<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
         dog_window45_argmax<float><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rect45(const WinArgs &a, int n, int pixel, cudaStream_t s)
+{
+    if (!a.h_taps) return cudaErrorInvalidValue;
+    Taps45 tp;
+    fold_taps(a, tp);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, vsm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&vsm, cudaDevAttrMultiProcessorCount, dev);
+        sms = vsm > 0 ? vsm : 148;
+    }
+    const int nty = (a.wr + WR - 1) / WR, ntx = (a.wc + WC - 1) / WC;
+    const long long items = (long long)n * nty * ntx;
+    // one CTA per SM; with fewer items than SMs every item gets an SM to itself (second halves stay idle)
+    const int grid = (int)std::max<long long>(1, std::min<long long>(sms, items));
+    const size_t smem = 2 * HALF_SMEM;
+    cudaError_t e;
+    if (pixel == 0) {
+        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect45_tiles<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
+        dog_rect45_tiles<uint8_t><<<grid, CTA_THREADS, smem, s>>>(a, tp, n, nty, ntx);
+    } else {
+        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect45_tiles<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
+        dog_rect45_tiles<float><<<grid, CTA_THREADS, smem, s>>>(a, tp, n, nty, ntx);
     }
     return cudaGetLastError();
 }
