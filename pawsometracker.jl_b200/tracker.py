@@ -186,9 +186,13 @@ class TrackerBatch:
                 flat.append(f.ctypes.data)
         return self.track_host_ptrs(flat, T, pitch, mode)
 
+    def make_ptr_table(self, ptrs):
+        """Pack frame addresses (T*n, step-major) into the C pointer table track_host_ptrs takes."""
+        return (C.c_void_p * len(ptrs))(*ptrs)
+
     def track_host_ptrs(self, ptrs, T: int, pitch: int, mode: str = "footprint"):
         m = {"footprint": 0, "frames": 1}[mode]
-        arr = (C.c_void_p * (T * self.n))(*ptrs)
+        arr = ptrs if isinstance(ptrs, C.Array) else (C.c_void_p * (T * self.n))(*ptrs)
         out = np.empty((T, self.n, 2), np.int32)
         resp = np.empty((T, self.n), np.float32)
         check(lib.pt_batch_track_host(self._h, arr, T, pitch, m, out.ctypes.data_as(_i32p), resp.ctypes.data_as(_fp)))

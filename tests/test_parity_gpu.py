@@ -365,6 +365,23 @@ def test_track_autodetect_and_batch_api(gpu_pkg, oracle):
         np.testing.assert_array_equal(singles[k], ref)
 
 
+def test_config2_1080p_autodetect_then_track(gpu_pkg, oracle):
+    """BASELINE config 2 (shortened): one 1080p video, start_location = missing → auto-detect over the
+    271×481 window centred on the frame (tile kernel), then windowed tracking; positions identical to the
+    oracle-driven loop and within 1 px RMS of the ground truth."""
+    H, W, nfr = 1080, 1920, 60
+    start = (540, 960)
+    tra = gpu_pkg.spiral(0.8 * 540, 3000, start, seed=0)[:nfr]          # the 3000-frame trajectory, first 60 frames
+    vid = gpu_pkg.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+    ts, ij = gpu_pkg.track(vid, stop=nfr / 24.0, target_width=25, start_location=None, fps=24)
+    assert len(ij) == nfr
+    frames = [vid.frame(k) for k in range(nfr)]
+    ref, near = oracle_track(oracle, frames, 25, True, (45, 45), None, autodetect=True)
+    assert near == 0
+    np.testing.assert_array_equal(ij, ref)
+    assert np.sqrt(np.mean(np.sum((ij - tra) ** 2, axis=1))) < 1.0
+
+
 def test_config5_segments_sar_start_fps(gpu_pkg, oracle):
     """Segmented multi-file video, SAR=2, (x,y) start, non-zero start, fps resampling
     (test/test-basic-test.jl:43-49, 73-79, 91-104, 116-121; src/PawsomeTracker.jl:181-214)."""
