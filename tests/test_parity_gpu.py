@@ -535,6 +535,35 @@ def test_guess_far_outside_frame(gpu_pkg, oracle):
             trk.close()
 
 
+def test_plain_c_consumer_of_the_abi(gpu_pkg, oracle, tmp_path):
+    """A C program compiled against include/pawsome.h and linked to libpawsome_cuda.so (no Python, no torch):
+    the drop-in boundary as a foreign binding sees it."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cabi_driver")
+    libdir = os.path.dirname(gpu_pkg.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cabi_driver.c"),
+                    "-o", exe, "-L", libdir, "-lpawsome_cuda", "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    T = 10
+    r = subprocess.run([exe, str(T)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[-1] == "ok" and lines[1] == "fill 128"
+    assert lines[0].split()[3] == "65" and lines[0].split()[5] == "45"
+    frames = []
+    for t in range(T):
+        frames.append(disk_frame(240, 320, 100 + 3 * t - 1, 150 + 5 * t - 1, 12))
+    ref, near = oracle_track(oracle, frames, 25, True, (45, 45), (97, 154))
+    assert near == 0
+    single = np.array([[int(x) for x in l.split()[2:4]] for l in lines if l.startswith("single")])
+    batch = np.array([[int(x) for x in l.split()[2:6]] for l in lines if l.startswith("batch")])
+    np.testing.assert_array_equal(single, ref)
+    np.testing.assert_array_equal(batch[:, :2], ref)
+    ref2, _ = oracle_track(oracle, frames, 25, True, (45, 45), (103, 146))
+    np.testing.assert_array_equal(batch[:, 2:], ref2)
+    np.testing.assert_array_equal(ref, np.array([[100 + 3 * t, 150 + 5 * t] for t in range(T)]))
+
+
 def test_error_behaviour(gpu_pkg):
     f = np.full((64, 64), 128, np.uint8)
     b = gpu_pkg.TrackerBatch(2, (64, 64), 10, (21, 21), True)
