@@ -349,14 +349,16 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         if (t + 1 < a.T && !a.frame_ptrs) {                      // (host frames are not cached in L2)
             const PixT *nframe = frame + a.step_stride;
             constexpr int PR = FR + WR - 1;                      // 153 rows
-            constexpr int NL = (int)(((FC + WC) * sizeof(PixT) + 127) / 128) + 1;   // 128-byte lines per row (3 for u8)
+            constexpr int NLMAX = (int)(((FC + WC) * sizeof(PixT) + 127) / 128) + 1;   // ≤ 3 lines per row for u8
             const int py0 = fy0 - WR / 2, pxb = (fx0 - WC / 2) * (int)sizeof(PixT);
+            const int line0 = pxb >> 7;
+            const int nl = ((pxb + (FC + WC - 1) * (int)sizeof(PixT) - 1) >> 7) - line0 + 1;   // exact: 2 or 3 for u8
             const int rowbytes = a.W * (int)sizeof(PixT);
-            for (int e = tid; e < PR * NL; e += THREADS) {
-                const int r = e / NL, ln = e - r * NL;
+            for (int e = tid; e < PR * NLMAX; e += THREADS) {
+                const int r = e / NLMAX, ln = e - r * NLMAX;
                 const int Y = py0 + r;
-                const int off = ((pxb >> 7) + ln) << 7;
-                if (Y >= 0 && Y < a.H && off >= 0 && off < rowbytes) {
+                const int off = (line0 + ln) << 7;
+                if (ln < nl && Y >= 0 && Y < a.H && off >= 0 && off < rowbytes) {
                     const char *ptr = reinterpret_cast<const char *>(nframe + (size_t)Y * a.pitch) + off;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
                 }
