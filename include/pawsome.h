@@ -201,6 +201,8 @@ PT_API int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int 
 /* FP32 FMA throughput of `device` in TFLOP/s (2 flops per FMA): packed=0 plain
  * FFMA, packed=1 fma.rn.f32x2.  The measured denominator of the FP32 roofline. */
 PT_API int pt_measure_fp32_peak(int device, int packed, int reps, double *tflops);
+/* Issue-port probe: time (ms) of a loop of packed FFMA2 with na ∈ {0,4,8} independent integer ops per 8 FFMA2. */
+PT_API int pt_probe_ffma2_issue(int device, int na, double *ms_out);
 /* Profiling aid: dog_window45_argmax writes (smid, clock64 at start / after stage / after row pass /
  * after column pass / end) per (video, step) into dev_buf ([n][T][6] int64); NULL switches it off. */
 PT_API int pt_debug_window45_timing(void *dev_buf);

@@ -74,6 +74,7 @@ SIGNATURES = {
     "pt_tracker_step_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int, _ip, _ip, _fp]),
     "pt_tracker_batch": (_vp, [_vp]),
     "pt_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "pt_probe_ffma2_issue": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pt_debug_window45_timing": (C.c_int, [_vp]),
     "pt_flush_l2": (C.c_int, [_vp, C.c_size_t, _vp]),
     "pt_batch_rect_argmax": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _fp]),

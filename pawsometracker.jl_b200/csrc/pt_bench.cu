@@ -59,6 +59,44 @@ __global__ void __launch_bounds__(256) fma_peak_packed(float *out, int iters, fl
     if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Issue-port probe: NF packed FFMA2 per NA independent integer ops (LOP3/IADD chains on other registers).
+// If FFMA2 held the dispatch port for both of its pipe cycles, adding ALU ops would lengthen the loop;
+// if they issue in its shadow, the time stays at the FFMA2-only value.
+template <int NA>
+__global__ void __launch_bounds__(256) ffma2_alu_mix(float *out, int iters, float a, float b)
+{
+    unsigned long long acc[8];
+    unsigned long long av, bv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+    unsigned int z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float x = (float)(threadIdx.x + i);
+        asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(x), "f"(x + 0.5f));
+        z[i] = threadIdx.x * 2654435761u + i;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(av), "l"(bv));
+                if (i < NA) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"(z[(i + 1) & 7]), "r"((unsigned)u));
+            }
+        }
+    }
+    float s = 0.f;
+    unsigned int zz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        s += lo + hi; zz ^= z[i];
+    }
+    if (s == 123.456f || zz == 0x12345u) out[blockIdx.x * blockDim.x + threadIdx.x] = s + (float)zz;
+}
+
 __global__ void flush_kernel(float4 *p, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,6 +137,36 @@ PT_API int pt_measure_fp32_peak(int device, int packed, int reps, double *tflops
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(out);
     *tflops = best;
+    return PT_OK;
+}
+
+// Issue-port probe (see ffma2_alu_mix): returns ms per launch for na ∈ {0, 4, 8} ALU ops per 8 FFMA2.
+PT_API int pt_probe_ffma2_issue(int device, int na, double *ms_out)
+{
+    if (!ms_out) return PT_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return PT_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PT_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+    float *out = nullptr;
+    if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return PT_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 1e30;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(e0);
+        if (na == 0) ffma2_alu_mix<0><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        else if (na == 4) ffma2_alu_mix<4><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        else ffma2_alu_mix<8><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return PT_ERR_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 1 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *ms_out = best;
     return PT_OK;
 }
 

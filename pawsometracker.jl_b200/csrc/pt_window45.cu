@@ -50,7 +50,10 @@ constexpr int NG = 5;                   // groups of R per 45
 constexpr int COL_ITEMS = WC * NG;      // 225 → 8 warp-tasks on 8 warps
 constexpr int RR = 5;                   // row pass: outputs per thread; 9 groups per row
 constexpr int ROW_ITEMS = FR * (WC / RR);   // 981 → 31 warp-tasks: 4 (or 3) per warp, 98.9 % lane fill
-constexpr int THREADS = 256;            // threads per window: 8 warps = 2 per SM sub-partition; row items take 3 rounds
+#ifndef PT_W45_THREADS
+#define PT_W45_THREADS 256
+#endif
+constexpr int THREADS = PT_W45_THREADS;  // threads per window: 8 warps = 2 per SM sub-partition
 constexpr int NWARPS = THREADS / 32;
 constexpr int CTA_THREADS = 2 * THREADS;   // two windows per CTA
 constexpr size_t HALF_SMEM = ((size_t)(FR * PIN + 1) * sizeof(float) + (size_t)FR * PM * sizeof(float2) + 15) & ~(size_t)15;
