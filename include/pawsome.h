@@ -197,6 +197,14 @@ PT_API pt_batch *pt_tracker_batch(pt_tracker *t);
 PT_API int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int wc,
                          int *oi, int *oj, int *raw_i, int *raw_j, float *resp);
 
+/* The same rectangle on the current frame of EVERY video of the batch in one launch
+ * (batched full-frame DoG; batched auto-detect, src/PawsomeTracker.jl:99-105).
+ * out_ij: [n][4] = (i, j clamped, raw i, raw j), 1-based; out_resp: [n].  With
+ * no_readback != 0 the call only enqueues the launch on the batch stream (results stay on the
+ * device; used to time the kernel alone) and the output pointers are ignored. */
+PT_API int pt_batch_rect_argmax_all(pt_batch *b, int y0, int x0, int wr, int wc,
+                             int32_t *out_ij, float *out_resp, int no_readback);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------- */
 /* FP32 FMA throughput of `device` in TFLOP/s (2 flops per FMA): packed=0 plain
  * FFMA, packed=1 fma.rn.f32x2.  The measured denominator of the FP32 roofline. */

@@ -78,6 +78,7 @@ SIGNATURES = {
     "pt_debug_window45_timing": (C.c_int, [_vp]),
     "pt_flush_l2": (C.c_int, [_vp, C.c_size_t, _vp]),
     "pt_batch_rect_argmax": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _fp]),
+    "pt_batch_rect_argmax_all": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _fp, C.c_int]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -953,6 +953,34 @@ int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int wc,
     return PT_OK;
 }
 
+int pt_batch_rect_argmax_all(pt_batch *b, int y0, int x0, int wr, int wc, int32_t *out_ij, float *out_resp, int no_readback)
+{
+    if (!b) return fail(PT_ERR_ARG, "batch is NULL");
+    if (wr < 1 || wc < 1) return fail(PT_ERR_ARG, "rectangle must be non-empty");
+    if ((long long)wr * wc > 0x7FFFFFFFll) return fail(PT_ERR_ARG, "rectangle too large");
+    int rc = set_device(b);
+    if (rc) return rc;
+    if (!b->fill_set) return fail(PT_ERR_STATE, "fill value not set");
+    const void *base; size_t stride, pitch;
+    rc = current_frames(b, &base, &stride, &pitch); if (rc) return rc;
+    pt::WinArgs a = make_args(b, base, stride, pitch, b->H, b->W, nullptr, b->n);
+    a.rect_mode = 1; a.ry0 = y0; a.rx0 = x0; a.wr = wr; a.wc = wc;
+    rc = launch_step(b, a, b->n, b->stream); if (rc) return rc;
+    if (no_readback) return PT_OK;
+    rc = b->h_out.ensure((size_t)b->n * 32); if (rc) return rc;
+    int4 *hp = reinterpret_cast<int4 *>(b->h_out.p);
+    float *hr = reinterpret_cast<float *>((char *)b->h_out.p + (size_t)b->n * 16);
+    CU(cudaMemcpyAsync(hp, b->d_pos, (size_t)b->n * sizeof(int4), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(hr, b->d_resp, (size_t)b->n * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    b->staging_busy = false;
+    for (int v = 0; v < b->n; ++v) {
+        if (out_ij) { out_ij[4 * v] = hp[v].x; out_ij[4 * v + 1] = hp[v].y; out_ij[4 * v + 2] = hp[v].z; out_ij[4 * v + 3] = hp[v].w; }
+        if (out_resp) out_resp[v] = hr[v];
+    }
+    return PT_OK;
+}
+
 long long pt_batch_launch_count(const pt_batch *b) { return b ? b->launches : 0; }
 
 const char *pt_batch_kernel_name(const pt_batch *b)

@@ -49,7 +49,7 @@ constexpr int R = 9;                    // column pass: outputs per thread along
 constexpr int NG = 5;                   // groups of R per 45
 constexpr int COL_ITEMS = WC * NG;      // 225 → 8 warp-tasks on 8 warps
 constexpr int RR = 5;                   // row pass: outputs per thread; 9 groups per row
-constexpr int ROW_ITEMS = FR * (WC / RR);   // 981 → 31 warp-tasks: 4 (or 3) per warp, 98.9 % lane fill
+// row pass items: FR * (WC / RR) = 981 → 31 warp-tasks: 4 (or 3) per warp, 98.9 % lane fill
 #ifndef PT_W45_THREADS
 #define PT_W45_THREADS 256
 #endif
@@ -99,22 +99,19 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 // ---- staging: footprint → smem as (pixel − fill), 0 outside the frame ----------------
 // Warp w takes rows w, w+9, …; every load of a thread is issued before the first
 // conversion so a frame that is cold in L2/HBM costs one memory round trip.
-template <typename PixT>
-__device__ __forceinline__ void stage_tile(const PixT *frame, int pitch, int H, int W, int fy0, int fx0,
-                                           float fill, float *s_in, int warp, int lane);
-
+// NROWS = rows staged into s_in rows 0..NROWS-1 (109 for a whole footprint, 45 for the next batch of a marching strip).
 // f32 frames: lane = column (+32q), coalesced 4-byte loads.
-template <>
-__device__ __forceinline__ void stage_tile<float>(const float *frame, int pitch, int H, int W, int fy0, int fx0,
-                                                  float fill, float *s_in, int warp, int lane)
+template <int NROWS>
+__device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H, int W, int fy0, int fx0,
+                                           float fill, float *s_in, int warp, int lane)
 {
-    constexpr int RPW = (FR + NWARPS - 1) / NWARPS;      // 13 rows per warp (last ones masked)
+    constexpr int RPW = (NROWS + NWARPS - 1) / NWARPS;   // 14 rows per warp for a footprint (last ones masked)
     float px[RPW][4];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
         const int Y = fy0 + f;
-        const bool yok = (f < FR) && (Y >= 0) && (Y < H);
+        const bool yok = (f < NROWS) && (Y >= 0) && (Y < H);
         const float *rowp = frame + (size_t)(yok ? Y : 0) * pitch;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -129,7 +126,7 @@ __device__ __forceinline__ void stage_tile<float>(const float *frame, int pitch,
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int c = lane + 32 * q;
-            if (f < FR && c < FC) s_in[f * PIN + c] = px[r][q] - fill;
+            if (f < NROWS && c < FC) s_in[f * PIN + c] = px[r][q] - fill;
         }
     }
 }
@@ -141,11 +138,11 @@ __device__ __forceinline__ void stage_tile<float>(const float *frame, int pitch,
 // exact.  Each lane rotates its word by lane/8 bytes so the four stores of a warp hit 32
 // distinct banks.  Requires frame base, pitch and strides to be multiples of 4 bytes and
 // pitch ≥ round_up(W, 4) (checked by window45_supported).
-template <bool kInterior>
-__device__ __forceinline__ void stage_tile_u8(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
+template <int NROWS, bool kInterior>
+__device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
                                               float fill, float *s_in, int warp, int lane)
 {
-    constexpr int RPW = (FR + NWARPS - 1) / NWARPS;
+    constexpr int RPW = (NROWS + NWARPS - 1) / NWARPS;
     const int xa = fx0 & ~3, phase = fx0 - xa;             // aligned start, phase 0..3
     const int X = xa + 4 * lane;                            // frame column of this lane's word
     const unsigned int fillw = (unsigned int)fill * 0x01010101u;
@@ -170,7 +167,7 @@ __device__ __forceinline__ void stage_tile_u8(const uint8_t *frame, int pitch, i
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
         const int Y = fy0 + f;
-        const bool ok = wordok && (f < FR) && (kInterior || ((Y >= 0) && (Y < H)));
+        const bool ok = wordok && (f < NROWS) && (kInterior || ((Y >= 0) && (Y < H)));
         wd[r] = fillw;
         if (ok) wd[r] = __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)(r * NWARPS) * pitch));
     }
@@ -178,7 +175,7 @@ __device__ __forceinline__ void stage_tile_u8(const uint8_t *frame, int pitch, i
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
-        if (f < FR) {
+        if (f < NROWS) {
             unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
             w = __funnelshift_r(w, w, 8 * rot);            // byte k of w = pixel (k + rot) & 3 of the word
             float *dst = s_in + f * PIN;
@@ -191,14 +188,21 @@ __device__ __forceinline__ void stage_tile_u8(const uint8_t *frame, int pitch, i
     }
 }
 
-template <>
-__device__ __forceinline__ void stage_tile<uint8_t>(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
-                                                    float fill, float *s_in, int warp, int lane)
+template <int NROWS>
+__device__ __forceinline__ void stage_rows(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
+                                           float fill, float *s_in, int warp, int lane)
 {
-    // interior: every aligned word the footprint touches lies inside the frame → no byte masks, no row checks
-    const bool interior = (fy0 >= 0) && (fy0 + FR <= H) && ((fx0 & ~3) >= 0) && ((fx0 & ~3) + 4 * 28 <= W);
-    if (interior) stage_tile_u8<true>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
-    else stage_tile_u8<false>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    // interior: every aligned word the rows touch lies inside the frame → no byte masks, no row checks
+    const bool interior = (fy0 >= 0) && (fy0 + NROWS <= H) && ((fx0 & ~3) >= 0) && ((fx0 & ~3) + 4 * 28 <= W);
+    if (interior) stage_rows_u8<NROWS, true>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    else stage_rows_u8<NROWS, false>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+}
+
+template <typename PixT>
+__device__ __forceinline__ void stage_tile(const PixT *frame, int pitch, int H, int W, int fy0, int fx0,
+                                           float fill, float *s_in, int warp, int lane)
+{
+    stage_rows<FR>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
 }
 
 } // namespace
@@ -206,11 +210,13 @@ __device__ __forceinline__ void stage_tile<uint8_t>(const uint8_t *frame, int pi
 
 // ---- row pass over one staged 109×109 tile: item = (footprint row f, group gq of 5 output columns);
 // lanes walk rows.  One FADD (symmetric fold) feeds one packed FFMA2 advancing (narrow, wide).
+// NROWS rows of s_in (from row 0) → NROWS rows of s_mid (from the pointer given).
+template <int NROWS = FR>
 __device__ __forceinline__ void row_pass45(const float *s_in, float2 *s_mid, int tid, const Taps45 &tp)
 {
 #pragma unroll 1
-    for (int item = tid; item < ROW_ITEMS; item += THREADS) {
-        const int gq = item / FR, f = item - gq * FR;
+    for (int item = tid; item < NROWS * (WC / RR); item += THREADS) {
+        const int gq = item / NROWS, f = item - gq * NROWS;
         const float *row = s_in + f * PIN + gq * RR;
         float x[RR + 2 * HW];
 #pragma unroll
@@ -423,15 +429,35 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
 
 // ---------------------------------------------------------------------------------------------------
 // Large rectangles at l = 65 (auto-detect window size .÷ 4, src/PawsomeTracker.jl:99-105; the full-frame
-// DoG benchmark shape; any non-default window_size at target_width 25): the output rectangle is cut into
-// 45×45 tiles and every tile is evaluated exactly like a window by one half-CTA (same staging, row pass,
-// column pass).  Tiles of a rectangle combine through one 64-bit atomicMax per (window, tile) and the
-// last tile decodes, clamps and publishes — the merge of the generic kernel.  Items = (window, tile);
-// half h of CTA c walks items c + S·h, c + S·(h+2), …; the row passes of the two halves alternate by token.
+// DoG benchmark shape; any non-default window_size at target_width 25).  The output rectangle is cut into
+// strips of 45 columns and every strip into `nchunks` runs of 45-row batches.  One half-CTA takes one
+// (window, chunk, strip) item and MARCHES down it:
+//   batch 0      stage the 109-row footprint, row pass over 109 rows, column pass → 45×45 outputs
+//                (exactly a window of dog_window45_argmax);
+//   batch b > 0  the last 64 rows of the row-pass intermediate are still valid: move them to the top of
+//                s_mid, stage only the 45 NEW footprint rows, row pass over those 45 rows, column pass.
+// So inside a chunk the row pass runs once per footprint row (the algorithmic count) instead of 109 rows
+// per 45 outputs; with nchunks = number of batches this degenerates to independent 45×45 tiles, which is
+// what small rectangles (fewer tiles than SMs) use.  The running argmax stays in registers across the
+// batches of an item; items of a rectangle combine through one 64-bit atomicMax per item and the last one
+// decodes, clamps and publishes — the merge of the generic kernel.  Half h of CTA c walks items c + S·h,
+// c + S·(h+2), …; the row passes of the two halves alternate by token as in dog_window45_argmax.
 // ---------------------------------------------------------------------------------------------------
+struct March45 {
+    int n, ntx, nty, nchunks;
+    int skew;
+};
+
+__device__ __forceinline__ void chunk_range(const March45 &m, int c, int &b0, int &nb)
+{
+    const int base = m.nty / m.nchunks, extra = m.nty - base * m.nchunks;
+    nb = base + (c < extra ? 1 : 0);
+    b0 = c * base + min(c, extra);
+}
+
 template <typename PixT>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
-dog_rect45_tiles(const __grid_constant__ WinArgs a, const __grid_constant__ Taps45 tp, int n, int nty, int ntx)
+dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps45 tp, const __grid_constant__ March45 m)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_keys[2][2 * NWARPS];
@@ -444,55 +470,101 @@ dog_rect45_tiles(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
     float2 *s_mid = reinterpret_cast<float2 *>(s_in + FR * PIN + 1);
     unsigned long long *s_key = s_keys[half];
     const int stride = 2 * (int)gridDim.x;
-    const int tiles = nty * ntx;
-    const long long items = (long long)n * tiles;
+    const int per_win = m.ntx * m.nchunks;
+    const long long items = (long long)m.n * per_win;
 
-    const int firstA = (int)blockIdx.x, firstB = (int)blockIdx.x + (int)gridDim.x;
-    const int NA = (firstA < items) ? (int)((items - 1 - firstA) / stride) + 1 : 0;
-    const int NB = (firstB < items) ? (int)((items - 1 - firstB) / stride) + 1 : 0;
-    const bool tokens = NB > 0;
-    int round = 0;
+    // number of row passes (= batches) each half will run: the token alternation stops cleanly
+    const long long firstA = (long long)blockIdx.x, firstB = (long long)blockIdx.x + gridDim.x;
+    int NA = 0, NB = 0;
+    for (long long it = firstA; it < items; it += stride) { int b0, nb; chunk_range(m, (int)(it % per_win) / m.ntx, b0, nb); NA += nb; }
+    for (long long it = firstB; it < items; it += stride) { int b0, nb; chunk_range(m, (int)(it % per_win) / m.ntx, b0, nb); NB += nb; }
+    const bool tokens = m.skew != 0 && NB > 0;
+    int round = 0, parity = 0;
 
-    for (long long item = (half ? firstB : firstA); item < items; item += stride, ++round) {
-        const int v = (int)(item / tiles), tl = (int)(item - (long long)v * tiles);
-        const int ty = tl / ntx, tx = tl - ty * ntx;
+    for (long long item = (half ? firstB : firstA); item < items; item += stride, parity ^= 1) {
+        const int v = (int)(item / per_win), rem = (int)(item - (long long)v * per_win);
+        const int c = rem / m.ntx, tx = rem - c * m.ntx;
+        int b0, nb;
+        chunk_range(m, c, b0, nb);
         int wy0, wx0;
         if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
         else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
-        const int gy0 = ty * WR, gx0 = tx * WC;
+        const int gx0 = tx * WC;
+        const int fx0 = wx0 + gx0 - HW;
         const float fill = a.fill[v];
         const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
-
-        stage_tile<PixT>(frame, a.pitch, a.H, a.W, wy0 + gy0 - HW, wx0 + gx0 - HW, fill, s_in, warp, lane);
-        bar_half(half);
-        if (tokens) {
-            if (half == 0) { if (round >= 1 && round - 1 < NB) asm volatile("bar.sync 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
-            else           { if (round < NA) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
-        }
-        row_pass45(s_in, s_mid, tid, tp);
-        bar_half(half);
-        if (tokens) {
-            if (half == 0) { if (round < NB) asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
-            else           { if (round + 1 < NA) asm volatile("bar.arrive 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
-        }
         float *map = a.map_out ? a.map_out + (size_t)v * a.wr * a.wc : nullptr;
-        unsigned long long key = col_pass45(s_mid, tid, tp, gy0, gx0, a.wr, a.wc, map);
+        unsigned long long best = 0ull;
+
+        for (int b = 0; b < nb; ++b, ++round) {
+            const int gy0 = (b0 + b) * WR;
+            float2 keep[(HW * 2 * WC + THREADS - 1) / THREADS];           // the 64 still-valid s_mid rows (2880 float2)
+            if (b == 0) {
+                stage_rows<FR>(frame, a.pitch, a.H, a.W, wy0 + gy0 - HW, fx0, fill, s_in, warp, lane);
+            } else {
+                stage_rows<WR>(frame, a.pitch, a.H, a.W, wy0 + gy0 + HW, fx0, fill, s_in, warp, lane);
+            }
+            // warm L2 with the 45 new footprint rows of the next batch
+            if (b + 1 < nb) {
+                constexpr int NL = (int)((FC * sizeof(PixT) + 127) / 128) + 1;
+                const int pxb = fx0 * (int)sizeof(PixT);
+                const int line0 = pxb >> 7;
+                const int nl = ((pxb + FC * (int)sizeof(PixT) - 1) >> 7) - line0 + 1;
+                const int rowbytes = a.W * (int)sizeof(PixT);
+                const int py0 = wy0 + gy0 + WR + HW;
+                for (int e = tid; e < WR * NL; e += THREADS) {
+                    const int r = e / NL, ln = e - r * NL;
+                    const int Y = py0 + r;
+                    const int off = (line0 + ln) << 7;
+                    if (ln < nl && Y >= 0 && Y < a.H && off >= 0 && off < rowbytes)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(frame + (size_t)Y * a.pitch) + off));
+                }
+            }
+            if (b > 0) {
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(keep) / sizeof(keep[0])); ++i) {
+                    const int e = tid + i * THREADS;
+                    if (e < 2 * HW * WC) keep[i] = s_mid[WR * PM + e];
+                }
+            }
+            bar_half(half);
+            if (b > 0) {
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(keep) / sizeof(keep[0])); ++i) {
+                    const int e = tid + i * THREADS;
+                    if (e < 2 * HW * WC) s_mid[e] = keep[i];
+                }
+            }
+            if (tokens) {
+                if (half == 0) { if (round >= 1 && round - 1 < NB) asm volatile("bar.sync 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
+                else           { if (round < NA) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
+            }
+            if (b == 0) row_pass45<FR>(s_in, s_mid, tid, tp);
+            else row_pass45<WR>(s_in, s_mid + 2 * HW * PM, tid, tp);
+            bar_half(half);
+            if (tokens) {
+                if (half == 0) { if (round < NB) asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
+                else           { if (round + 1 < NA) asm volatile("bar.arrive 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
+            }
+            const unsigned long long key = col_pass45(s_mid, tid, tp, gy0, gx0, a.wr, a.wc, map);
+            best = key > best ? key : best;
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
-            key = o > key ? o : key;
+            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+            best = o > best ? o : best;
         }
-        if (lane == 0) s_key[(round & 1) * NWARPS + warp] = key;
-        bar_half(half);
+        if (lane == 0) s_key[parity * NWARPS + warp] = best;
+        bar_half(half);      // also: every column-pass read of s_mid is done before the next item's row pass
         if (tid == 0) {
-            const unsigned long long *kk = s_key + (round & 1) * NWARPS;
+            const unsigned long long *kk = s_key + parity * NWARPS;
             unsigned long long k = kk[0];
 #pragma unroll
             for (int i = 1; i < NWARPS; ++i) k = kk[i] > k ? kk[i] : k;
             atomicMax(a.keys + v, k);
             __threadfence();
             const unsigned int prev = atomicAdd(a.counters + v, 1u);
-            if (prev == (unsigned int)tiles - 1u) {
+            if (prev == (unsigned int)per_win - 1u) {
                 __threadfence();
                 const unsigned long long win = atomicExch(a.keys + v, 0ull);
                 a.counters[v] = 0u;
@@ -502,7 +574,7 @@ dog_rect45_tiles(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
     }
 }
 
-const char *rect45_name() { return "dog_rect45_tiles"; }
+const char *rect45_name() { return "dog_rect45_march"; }
 
 bool rect45_supported(const WinArgs &a, int pixel)
 {
@@ -587,6 +659,26 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// Decomposition of an output rectangle: how many chunks per strip.  Cost model in units of one marching
+// batch on a shared SM (measured, profiles/): first batch of an item ≈ 1.75 (it stages and row-filters the
+// whole 109-row footprint), later batches 1; an item alone on its SM runs ≈ 1.6× faster than a pair.
+int rect45_pick_chunks(int n, int ntx, int nty, int sms)
+{
+    if (const char *e = getenv("PT_R45_CHUNKS")) { const int c = atoi(e); if (c >= 1) return std::min(c, nty); }
+    int best_c = nty;
+    double best_cost = 1e300;
+    for (int c = 1; c <= nty; ++c) {
+        const long long items = (long long)n * ntx * c;
+        const int nbmax = (nty + c - 1) / c;
+        const double item_cost = 1.75 + (nbmax - 1);
+        double cost;
+        if (items <= sms) cost = item_cost / 1.6;
+        else cost = (double)((items + 2LL * sms - 1) / (2LL * sms)) * item_cost;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_c = c; }
+    }
+    return best_c;
+}
+
 cudaError_t launch_rect45(const WinArgs &a, int n, int pixel, cudaStream_t s)
 {
     if (!a.h_taps) return cudaErrorInvalidValue;
@@ -599,18 +691,27 @@ cudaError_t launch_rect45(const WinArgs &a, int n, int pixel, cudaStream_t s)
         cudaDeviceGetAttribute(&vsm, cudaDevAttrMultiProcessorCount, dev);
         sms = vsm > 0 ? vsm : 148;
     }
-    const int nty = (a.wr + WR - 1) / WR, ntx = (a.wc + WC - 1) / WC;
-    const long long items = (long long)n * nty * ntx;
+    March45 m;
+    m.n = n;
+    m.nty = (a.wr + WR - 1) / WR;
+    m.ntx = (a.wc + WC - 1) / WC;
+    m.nchunks = rect45_pick_chunks(n, m.ntx, m.nty, sms);
+    {
+        static int skew = -1;
+        if (skew < 0) { const char *e2 = getenv("PT_R45_SKEW"); skew = e2 ? atoi(e2) : 1; }
+        m.skew = skew;
+    }
+    const long long items = (long long)n * m.ntx * m.nchunks;
     // one CTA per SM; with fewer items than SMs every item gets an SM to itself (second halves stay idle)
     const int grid = (int)std::max<long long>(1, std::min<long long>(sms, items));
     const size_t smem = 2 * HALF_SMEM;
     cudaError_t e;
     if (pixel == 0) {
-        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect45_tiles<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-        dog_rect45_tiles<uint8_t><<<grid, CTA_THREADS, smem, s>>>(a, tp, n, nty, ntx);
+        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect45_march<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
+        dog_rect45_march<uint8_t><<<grid, CTA_THREADS, smem, s>>>(a, tp, m);
     } else {
-        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect45_tiles<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-        dog_rect45_tiles<float><<<grid, CTA_THREADS, smem, s>>>(a, tp, n, nty, ntx);
+        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect45_march<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
+        dog_rect45_march<float><<<grid, CTA_THREADS, smem, s>>>(a, tp, m);
     }
     return cudaGetLastError();
 }

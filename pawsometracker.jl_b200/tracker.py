@@ -211,6 +211,18 @@ class TrackerBatch:
                                        C.byref(ri), C.byref(rj), C.byref(r)))
         return (oi.value, oj.value), (ri.value, rj.value), r.value
 
+    def rect_argmax_all(self, y0: int, x0: int, wr: int, wc: int, readback: bool = True):
+        """The same output rectangle on the current frame of every video, one launch.  Returns
+        (ij [n,2], raw_ij [n,2], resp [n]); with readback=False only enqueues the launch."""
+        if not readback:
+            check(lib.pt_batch_rect_argmax_all(self._h, int(y0), int(x0), int(wr), int(wc), None, None, 1))
+            return None
+        out = np.empty((self.n, 4), np.int32)
+        resp = np.empty(self.n, np.float32)
+        check(lib.pt_batch_rect_argmax_all(self._h, int(y0), int(x0), int(wr), int(wc),
+                                           out.ctypes.data_as(C.POINTER(C.c_int32)), resp.ctypes.data_as(_fp), 0))
+        return out[:, :2].copy(), out[:, 2:].copy(), resp
+
     # -- introspection -----------------------------------------------------------
     @property
     def launch_count(self) -> int:

@@ -243,6 +243,57 @@ def test_full_frame_rect_1080p(gpu_pkg, oracle):
         b.close()
 
 
+@pytest.mark.parametrize("chunks", ["1", "2", "3", "5", "99"])
+def test_marching_rect_kernel_chunkings(gpu_pkg, oracle, monkeypatch, chunks):
+    """dog_rect45_march: a strip is cut into `chunks` runs of 45-row batches; inside a run the row-pass
+    intermediate is carried from batch to batch.  Every chunking must give the same response map (bit for
+    bit — the same operations in the same order) and that map must match the oracle; the window hangs over
+    two frame edges so the marching staging path meets rows and columns outside the frame."""
+    rng = np.random.default_rng(21)
+    f = rng.integers(0, 256, (300, 280)).astype(np.uint8)
+    ws, guess = (231, 200), (190, 60)           # 231x201 outputs = 6x5 tiles; rows 75..305, cols -40..160
+    monkeypatch.setenv("PT_R45_CHUNKS", chunks)
+    trk = gpu_pkg.Tracker(f, 25, ws, False)
+    try:
+        fill = oracle.mode(f)
+        assert trk.fillvalue == fill
+        ref = oracle.step(f, fill, 25, False, ws, guess, dense=False, want_map=True)
+        got = trk.step_resident(guess)
+        resp = trk.last_response
+        rmap = trk.response_map(guess)
+        assert rmap.shape == ref.R.shape == (231, 201)
+        assert np.abs(rmap.astype(np.float64) - ref.R).max() <= RTOL * ref.maxabs
+        assert abs(resp - ref.resp) <= RTOL * ref.maxabs
+        assert not ref.near_tie(RTOL)
+        assert got == (ref.i, ref.j)
+        # the published maximum is the maximum of the published map, at findmax's first position
+        jj, ii = np.unravel_index(np.argmax(rmap.T), rmap.T.shape)
+        assert resp == rmap[ii, jj]
+        monkeypatch.setenv("PT_R45_CHUNKS", "99")               # independent tiles
+        assert np.array_equal(trk.response_map(guess), rmap)
+    finally:
+        trk.close()
+
+
+def test_marching_rect_batch_of_frames(gpu_pkg, oracle):
+    """Several 600x500 frames auto-detected in one launch (items = window x chunk x strip)."""
+    rng = np.random.default_rng(4)
+    H, W, n = 600, 500, 5
+    cents = [(int(rng.integers(230, 370)), int(rng.integers(190, 310))) for _ in range(n)]
+    frames = [disk_frame(H, W, cy, cx, 12) for cy, cx in cents]
+    b = gpu_pkg.TrackerBatch(n, (H, W), 25, (H // 4, W // 4), True)
+    try:
+        b.set_frames(frames)
+        b.compute_fill()
+        ij, resp = b.step([[H // 2, W // 2]] * n)
+        for v in range(n):
+            ref = oracle.step(frames[v], 128, 25, True, (H // 4, W // 4), (H // 2, W // 2), dense=False)
+            assert tuple(ij[v]) == (ref.i, ref.j) == (cents[v][0] + 1, cents[v][1] + 1)
+            assert abs(resp[v] - ref.resp) <= RTOL * ref.maxabs
+    finally:
+        b.close()
+
+
 # ---------------------------------------------------------------------------
 def oracle_track(oracle, frames, tw, darker, ws, start_guess, autodetect=False):
     """The intended frame loop (src/PawsomeTracker.jl:159-169) driven by the oracle."""
