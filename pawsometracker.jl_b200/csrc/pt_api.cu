@@ -222,7 +222,7 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     a.rr = b->rr; a.rc = b->rc; a.wr = b->wr; a.wc = b->wc;
     a.L = b->L; a.w = b->w; a.Lpad = b->Lpad;
     a.taps_row = b->d_taps_row; a.taps_col = b->d_taps_col;
-    a.keys = b->d_keys; a.counters = b->d_counters;
+    a.keys = b->d_keys; a.counters = b->d_counters; a.tickets = b->d_counters + b->n;
     a.out_pos = b->d_pos; a.out_resp = b->d_resp;
     a.next_guess = nullptr; a.traj_pos = nullptr; a.traj_resp = nullptr; a.map_out = nullptr;
     a.T = 1; a.step_stride = 0;
@@ -461,7 +461,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     cu(cudaMalloc(&b->d_guess, sizeof(int2) * n), "cudaMalloc guess");
     cu(cudaMalloc(&b->d_center, sizeof(int2) * n), "cudaMalloc center");
     cu(cudaMalloc(&b->d_keys, sizeof(unsigned long long) * n), "cudaMalloc keys");
-    cu(cudaMalloc(&b->d_counters, sizeof(unsigned int) * n), "cudaMalloc counters");
+    cu(cudaMalloc(&b->d_counters, sizeof(unsigned int) * 3 * n), "cudaMalloc counters");   // [n] completion + [n][2] ticket scratch
     cu(cudaMalloc(&b->d_hist, sizeof(unsigned int) * 512 * (size_t)n), "cudaMalloc hist");
     cu(cudaMalloc(&b->d_pos, sizeof(int4) * n), "cudaMalloc pos");
     cu(cudaMalloc(&b->d_resp, sizeof(float) * n), "cudaMalloc resp");
@@ -469,7 +469,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
         cu(cudaMemcpy(b->d_taps_row, trow.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
         cu(cudaMemcpy(b->d_taps_col, tcol.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
         cu(cudaMemset(b->d_keys, 0, sizeof(unsigned long long) * n), "memset");
-        cu(cudaMemset(b->d_counters, 0, sizeof(unsigned int) * n), "memset");
+        cu(cudaMemset(b->d_counters, 0, sizeof(unsigned int) * 3 * n), "memset");
         cu(cudaMemset(b->d_hist, 0, sizeof(unsigned int) * 512 * (size_t)n), "memset");
         cu(cudaMemset(b->d_pos, 0, sizeof(int4) * n), "memset");
         cu(cudaMemset(b->d_resp, 0, sizeof(float) * n), "memset");
@@ -735,7 +735,7 @@ void lane_worker(HostTrack *ht, pt_lane *ln)
         if (e == cudaSuccess) {
             pt::WinArgs a = make_args(b, ln->d_crops.p, crop_elems, cp, fr, fc, b->d_center + ln->v0, nl);
             a.fill = b->d_fill + ln->v0;
-            a.keys = b->d_keys + ln->v0; a.counters = b->d_counters + ln->v0;
+            a.keys = b->d_keys + ln->v0; a.counters = b->d_counters + ln->v0; a.tickets = b->d_counters + b->n + 2 * ln->v0;
             a.out_pos = b->d_pos + ln->v0; a.out_resp = b->d_resp + ln->v0;
             e = launch_windows(b, a, nl, ln->stream);
         }
@@ -914,7 +914,7 @@ int pt_batch_response_map(pt_batch *b, int v, int gi, int gj, float *out_map)
     const size_t es = px_size(b->pixel);
     pt::WinArgs a = make_args(b, (const char *)base + (size_t)v * stride * es, stride, pitch, b->H, b->W, nullptr, 1);
     a.rect_mode = 1; a.ry0 = gi - 1 - b->rr; a.rx0 = gj - 1 - b->rc;
-    a.fill = b->d_fill + v; a.keys = b->d_keys + v; a.counters = b->d_counters + v;
+    a.fill = b->d_fill + v; a.keys = b->d_keys + v; a.counters = b->d_counters + v; a.tickets = b->d_counters + b->n + 2 * v;
     a.out_pos = b->d_pos + v; a.out_resp = b->d_resp + v;
     a.map_out = (float *)b->d_map.p;
     rc = launch_step(b, a, 1, b->stream); if (rc) return rc;
@@ -938,7 +938,7 @@ int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int wc,
     const size_t es = px_size(b->pixel);
     pt::WinArgs a = make_args(b, (const char *)base + (size_t)v * stride * es, stride, pitch, b->H, b->W, nullptr, 1);
     a.rect_mode = 1; a.ry0 = y0; a.rx0 = x0; a.wr = wr; a.wc = wc;
-    a.fill = b->d_fill + v; a.keys = b->d_keys + v; a.counters = b->d_counters + v;
+    a.fill = b->d_fill + v; a.keys = b->d_keys + v; a.counters = b->d_counters + v; a.tickets = b->d_counters + b->n + 2 * v;
     a.out_pos = b->d_pos + v; a.out_resp = b->d_resp + v;
     rc = launch_step(b, a, 1, b->stream); if (rc) return rc;
     rc = b->h_out.ensure((size_t)b->n * 32); if (rc) return rc;

@@ -30,6 +30,7 @@ struct WinArgs {
     int strips, chunks, CH;    // CTA decomposition of one window
     unsigned long long *keys;  // [n] packed running argmax (zero between launches)
     unsigned int *counters;    // [n] CTA completion counters (zero between launches)
+    unsigned int *tickets;     // [2] work-ticket counter + finished-halves counter of dog_rect45_march (zero between launches)
     int4 *out_pos;             // [n] (i, j clamped; raw_i, raw_j), 1-based
     float *out_resp;           // [n] maximum response
     int2 *next_guess;          // [n] clamped result for the next chained step (may alias guess)

@@ -441,11 +441,11 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
 // what small rectangles (fewer tiles than SMs) use.  The running argmax stays in registers across the
 // batches of an item; items of a rectangle combine through one 64-bit atomicMax per item and the last one
 // decodes, clamps and publishes — the merge of the generic kernel.  Half h of CTA c walks items c + S·h,
-// c + S·(h+2), …; the row passes of the two halves alternate by token as in dog_window45_argmax.
+// then whatever the ticket counter hands it (the token alternation of dog_window45_argmax made no measurable
+// difference here — both phases of a marching batch are FMA-heavy — and is not used).
 // ---------------------------------------------------------------------------------------------------
 struct March45 {
     int n, ntx, nty, nchunks;
-    int skew;
 };
 
 __device__ __forceinline__ void chunk_range(const March45 &m, int c, int &b0, int &nb)
@@ -460,7 +460,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1)
 dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps45 tp, const __grid_constant__ March45 m)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long s_keys[2][2 * NWARPS];
+    __shared__ unsigned long long s_keys[2][NWARPS];
+    __shared__ unsigned int s_ticket[2];
 
     const int pw = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = (pw >> 2) & 1;
@@ -469,20 +470,20 @@ dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
     float *s_in = reinterpret_cast<float *>(smem_raw + half * HALF_SMEM);
     float2 *s_mid = reinterpret_cast<float2 *>(s_in + FR * PIN + 1);
     unsigned long long *s_key = s_keys[half];
-    const int stride = 2 * (int)gridDim.x;
     const int per_win = m.ntx * m.nchunks;
-    const long long items = (long long)m.n * per_win;
+    const unsigned int items = (unsigned int)m.n * (unsigned int)per_win;
 
-    // number of row passes (= batches) each half will run: the token alternation stops cleanly
-    const long long firstA = (long long)blockIdx.x, firstB = (long long)blockIdx.x + gridDim.x;
-    int NA = 0, NB = 0;
-    for (long long it = firstA; it < items; it += stride) { int b0, nb; chunk_range(m, (int)(it % per_win) / m.ntx, b0, nb); NA += nb; }
-    for (long long it = firstB; it < items; it += stride) { int b0, nb; chunk_range(m, (int)(it % per_win) / m.ntx, b0, nb); NB += nb; }
-    const bool tokens = m.skew != 0 && NB > 0;
-    int round = 0, parity = 0;
+    // Items are handed out by a ticket counter: a half that shares its SM runs ≈ 1.6× slower than one
+    // that has the SM to itself, so a static split would leave SMs idle at the end.  The first two
+    // tickets of a CTA are static (CTA c: c and S + c); the ticket of the NEXT item is fetched while the
+    // current one is processed, so its latency is never exposed.
+    unsigned int item = (unsigned int)blockIdx.x + (unsigned int)gridDim.x * (unsigned int)half;
+    const unsigned int static_items = 2u * gridDim.x;
 
-    for (long long item = (half ? firstB : firstA); item < items; item += stride, parity ^= 1) {
-        const int v = (int)(item / per_win), rem = (int)(item - (long long)v * per_win);
+    while (item < items) {
+        unsigned int next = 0u;
+        if (tid == 0) next = static_items + atomicAdd(a.tickets, 1u);
+        const int v = (int)(item / (unsigned int)per_win), rem = (int)(item - (unsigned int)v * (unsigned int)per_win);
         const int c = rem / m.ntx, tx = rem - c * m.ntx;
         int b0, nb;
         chunk_range(m, c, b0, nb);
@@ -496,14 +497,12 @@ dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
         float *map = a.map_out ? a.map_out + (size_t)v * a.wr * a.wc : nullptr;
         unsigned long long best = 0ull;
 
-        for (int b = 0; b < nb; ++b, ++round) {
+        for (int b = 0; b < nb; ++b) {
             const int gy0 = (b0 + b) * WR;
-            float2 keep[(HW * 2 * WC + THREADS - 1) / THREADS];           // the 64 still-valid s_mid rows (2880 float2)
-            if (b == 0) {
-                stage_rows<FR>(frame, a.pitch, a.H, a.W, wy0 + gy0 - HW, fx0, fill, s_in, warp, lane);
-            } else {
-                stage_rows<WR>(frame, a.pitch, a.H, a.W, wy0 + gy0 + HW, fx0, fill, s_in, warp, lane);
-            }
+            constexpr int NKEEP = (2 * HW * WC + THREADS - 1) / THREADS;
+            float2 keep[NKEEP];                                          // the 64 still-valid s_mid rows (2880 float2)
+            if (b == 0) stage_rows<FR>(frame, a.pitch, a.H, a.W, wy0 + gy0 - HW, fx0, fill, s_in, warp, lane);
+            else stage_rows<WR>(frame, a.pitch, a.H, a.W, wy0 + gy0 + HW, fx0, fill, s_in, warp, lane);
             // warm L2 with the 45 new footprint rows of the next batch
             if (b + 1 < nb) {
                 constexpr int NL = (int)((FC * sizeof(PixT) + 127) / 128) + 1;
@@ -522,30 +521,23 @@ dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
             }
             if (b > 0) {
 #pragma unroll
-                for (int i = 0; i < (int)(sizeof(keep) / sizeof(keep[0])); ++i) {
+                for (int i = 0; i < NKEEP; ++i) {
                     const int e = tid + i * THREADS;
                     if (e < 2 * HW * WC) keep[i] = s_mid[WR * PM + e];
                 }
             }
             bar_half(half);
-            if (b > 0) {
+            if (b == 0) {
+                row_pass45<FR>(s_in, s_mid, tid, tp);
+            } else {
 #pragma unroll
-                for (int i = 0; i < (int)(sizeof(keep) / sizeof(keep[0])); ++i) {
+                for (int i = 0; i < NKEEP; ++i) {
                     const int e = tid + i * THREADS;
                     if (e < 2 * HW * WC) s_mid[e] = keep[i];
                 }
+                row_pass45<WR>(s_in, s_mid + 2 * HW * PM, tid, tp);
             }
-            if (tokens) {
-                if (half == 0) { if (round >= 1 && round - 1 < NB) asm volatile("bar.sync 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
-                else           { if (round < NA) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
-            }
-            if (b == 0) row_pass45<FR>(s_in, s_mid, tid, tp);
-            else row_pass45<WR>(s_in, s_mid + 2 * HW * PM, tid, tp);
             bar_half(half);
-            if (tokens) {
-                if (half == 0) { if (round < NB) asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
-                else           { if (round + 1 < NA) asm volatile("bar.arrive 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
-            }
             const unsigned long long key = col_pass45(s_mid, tid, tp, gy0, gx0, a.wr, a.wc, map);
             best = key > best ? key : best;
         }
@@ -554,13 +546,14 @@ dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
             const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, best, off);
             best = o > best ? o : best;
         }
-        if (lane == 0) s_key[parity * NWARPS + warp] = best;
+        if (lane == 0) s_key[warp] = best;
+        if (tid == 0) s_ticket[half] = next;
         bar_half(half);      // also: every column-pass read of s_mid is done before the next item's row pass
+        item = s_ticket[half];
         if (tid == 0) {
-            const unsigned long long *kk = s_key + parity * NWARPS;
-            unsigned long long k = kk[0];
+            unsigned long long k = s_key[0];
 #pragma unroll
-            for (int i = 1; i < NWARPS; ++i) k = kk[i] > k ? kk[i] : k;
+            for (int i = 1; i < NWARPS; ++i) k = s_key[i] > k ? s_key[i] : k;
             atomicMax(a.keys + v, k);
             __threadfence();
             const unsigned int prev = atomicAdd(a.counters + v, 1u);
@@ -571,6 +564,13 @@ dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
                 publish_result(a, v, win, wy0, wx0);
             }
         }
+        // (s_key is rewritten only after the next item's barriers, which thread 0 has to pass too)
+    }
+    // leave the ticket counter zeroed for the next launch: the last half to run out of work resets it
+    // (every half has fetched its final, failing ticket by then)
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(a.tickets + 1, 1u);
+        if (prev == 2u * gridDim.x - 1u) { a.tickets[0] = 0u; a.tickets[1] = 0u; __threadfence(); }
     }
 }
 
@@ -660,8 +660,11 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
 }
 
 // Decomposition of an output rectangle: how many chunks per strip.  Cost model in units of one marching
-// batch on a shared SM (measured, profiles/): first batch of an item ≈ 1.75 (it stages and row-filters the
-// whole 109-row footprint), later batches 1; an item alone on its SM runs ≈ 1.6× faster than a pair.
+// batch on a shared SM (≈ 6.3 µs measured, tools/rect_timing.py): the first batch of an item ≈ 1.75 (it stages
+// and row-filters the whole 109-row footprint), later batches 1; an item alone on its SM runs ≈ 1.6× faster than
+// a pair.  Measured behaviour of the ticket scheduler: the halves of an SM finish together and fetch together, so
+// with few rounds the makespan is ceil(items / 2·SMs) whole items; with many rounds it tends to
+// total work / (2·SMs) plus half an item of tail.
 int rect45_pick_chunks(int n, int ntx, int nty, int sms)
 {
     if (const char *e = getenv("PT_R45_CHUNKS")) { const int c = atoi(e); if (c >= 1) return std::min(c, nty); }
@@ -671,9 +674,12 @@ int rect45_pick_chunks(int n, int ntx, int nty, int sms)
         const long long items = (long long)n * ntx * c;
         const int nbmax = (nty + c - 1) / c;
         const double item_cost = 1.75 + (nbmax - 1);
+        const double work = (double)n * ntx * (1.75 * c + (nty - c));
+        const double rounds = (double)items / (2.0 * sms);
         double cost;
         if (items <= sms) cost = item_cost / 1.6;
-        else cost = (double)((items + 2LL * sms - 1) / (2LL * sms)) * item_cost;
+        else if (rounds <= 4.0) cost = (double)((items + 2LL * sms - 1) / (2LL * sms)) * item_cost;
+        else cost = work / (2.0 * sms) + 0.5 * item_cost;
         if (cost < best_cost - 1e-9) { best_cost = cost; best_c = c; }
     }
     return best_c;
@@ -696,11 +702,6 @@ cudaError_t launch_rect45(const WinArgs &a, int n, int pixel, cudaStream_t s)
     m.nty = (a.wr + WR - 1) / WR;
     m.ntx = (a.wc + WC - 1) / WC;
     m.nchunks = rect45_pick_chunks(n, m.ntx, m.nty, sms);
-    {
-        static int skew = -1;
-        if (skew < 0) { const char *e2 = getenv("PT_R45_SKEW"); skew = e2 ? atoi(e2) : 1; }
-        m.skew = skew;
-    }
     const long long items = (long long)n * m.ntx * m.nchunks;
     // one CTA per SM; with fewer items than SMs every item gets an SM to itself (second halves stay idle)
     const int grid = (int)std::max<long long>(1, std::min<long long>(sms, items));
