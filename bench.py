@@ -365,6 +365,25 @@ def run_gpu(args, ranks):
     world = ranks.world
     value = world * n * K / (ms_K * 1e-3)
 
+    # ---- mode(frame) = fill value of each video's first frame (src/PawsomeTracker.jl:47): one HBM pass
+    pkg.lib.pt_flush_l2(flush.data_ptr(), flush.numel(), batch.stream)
+    md = []
+    for k in range(3):
+        batch.bind_device_frames(ring.data_ptr() + ((k + 1) % slots) * step_stride, H * W, W)   # a slot not in L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        with torch.cuda.stream(ext):
+            e0.record()
+            fk = batch.compute_fill()
+            e1.record()
+        torch.cuda.synchronize(device)
+        md.append(e0.elapsed_time(e1))
+        assert (fk == 128).all()
+    batch.bind_device_frames(ring.data_ptr(), H * W, W)
+    mode_t = float(np.min(md)) * 1e-3
+    mode_fill = {"ms": mode_t * 1e3, "frames": n, "bytes": n * H * W, "gb_per_s": n * H * W / mode_t / 1e9,
+                 "note": "256-bin mode of 256 1080p u8 frames (StatsBase tie rule), incl. the read-back of the fills"}
+
     # ---- supplementary: the same step with 2 videos per SM (grid = a whole multiple of the SM count).
     # 256 videos on 148 SMs leave 40 SMs with one window while 108 carry two and set the launch time;
     # this shows the kernel's rate when the batch fills every SM evenly.  Not the BASELINE config.
@@ -414,6 +433,12 @@ def run_gpu(args, ranks):
 
     # ---- FP32 peak (measured) and roofline of the dominant kernel
     import ctypes as C
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tf = C.c_double()
     tf2 = C.c_double()
     pkg._lib.check(pkg.lib.pt_measure_fp32_peak(dev_index, 0, 5, C.byref(tf)))
@@ -421,6 +446,7 @@ def run_gpu(args, ranks):
     fp32_peak = max(tf.value, tf2.value)
     if balanced:
         balanced["frac_fp32"] = balanced["achieved_tflops"] / fp32_peak
+    mode_fill["frac_hbm"] = mode_fill["gb_per_s"] / hbm_peak
     alg = algorithmic_per_window()
     launch_s = ms_K * 1e-3 / max(1, timed_launches)          # the dominant kernel chains K steps per launch
     steps_per_launch = K / max(1, timed_launches)
@@ -428,12 +454,6 @@ def run_gpu(args, ranks):
     bytes_launch = steps_per_launch * n * alg["bytes"]
     ach_tflops = flops_launch / launch_s / 1e12
     ach_gbs = bytes_launch / launch_s / 1e9
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     t_roof = max(flops_launch / (fp32_peak * 1e12), bytes_launch / (hbm_peak * 1e9))
     # DRAM traffic of this kernel from profiles/r01_window45_final_ncu_full_selected.csv (one `ncu --set full`
     # capture of a 20-step launch: dram read 209.1 MB + write 5.0 MB): 10.70 MB per 256-video step
@@ -572,7 +592,7 @@ def run_gpu(args, ranks):
                                   f"since the previous repeat; ring of {slots} slots; L2 flushed between repeats",
                                timing="CUDA events on the launching stream, median over repeats, max over ranks"),
                 "clocks": clocks, "e2e": e2e, "e2e_frames": e2e_frames, "roofline": roofline,
-                "cpu_baseline": cpu, "fullframe_dog": fullframe, "balanced_batch": balanced,
+                "cpu_baseline": cpu, "fullframe_dog": fullframe, "balanced_batch": balanced, "mode_fill": mode_fill,
                 "gpu_launches": int(timed_launches),
                 "gpu_launches_note": f"{batch_kernel} chains the K steps of the timed region inside "
                                      f"{int(timed_launches)} launch(es) (one CTA per SM hosts two videos; the serial "

@@ -171,6 +171,11 @@ struct pt_batch {
     std::vector<float> h_taps;           // host copy: row narrow | row wide | col narrow | col wide, each L
     int2 *d_guess = nullptr;
     bool guess_set = false;
+    // host mirror of the chain state: valid ⇒ h_guess equals what the next step must start from;
+    // d_guess_stale ⇒ the device copy is older than the mirror and is refreshed before any device-side use
+    std::vector<int32_t> h_guess;
+    bool h_guess_valid = false, d_guess_stale = false;
+    int center_key[3] = {-1, -1, -1};    // (rr, rc, w) d_center was last filled for
     bool staging_busy = false;           // an async H2D from the guess staging may be in flight
     int2 *d_center = nullptr;            // crop-mode guess: centre of the footprint
     unsigned long long *d_keys = nullptr;
@@ -307,7 +312,25 @@ int upload_guess(pt_batch *b, const int32_t *g, cudaStream_t s)
     CU(cudaMemcpyAsync(b->d_guess, st, sizeof(int2) * (size_t)b->n, cudaMemcpyHostToDevice, s));
     b->guess_set = true;
     b->staging_busy = true;
+    if (g != b->h_guess.data()) b->h_guess.assign(g, g + 2 * (size_t)b->n);
+    b->h_guess_valid = true;
+    b->d_guess_stale = false;
     return PT_OK;
+}
+
+// Before any kernel reads d_guess: bring the device copy up to date with the host mirror.
+int flush_guess(pt_batch *b, cudaStream_t s = nullptr)
+{
+    if (!b->d_guess_stale) return PT_OK;
+    return upload_guess(b, b->h_guess.data(), s ? s : b->stream);
+}
+
+// After a step whose clamped results were read back into out_ij (n×2): they are the next chain state.
+void mirror_from_results(pt_batch *b, const int32_t *out_ij)
+{
+    if (out_ij) { b->h_guess.assign(out_ij, out_ij + 2 * (size_t)b->n); b->h_guess_valid = true; }
+    else b->h_guess_valid = false;
+    b->d_guess_stale = false;
 }
 
 // Copy n host frames into d_frames[slot] on stream s, through pinned staging
@@ -462,7 +485,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     cu(cudaMalloc(&b->d_center, sizeof(int2) * n), "cudaMalloc center");
     cu(cudaMalloc(&b->d_keys, sizeof(unsigned long long) * n), "cudaMalloc keys");
     cu(cudaMalloc(&b->d_counters, sizeof(unsigned int) * 3 * n), "cudaMalloc counters");   // [n] completion + [n][2] ticket scratch
-    cu(cudaMalloc(&b->d_hist, sizeof(unsigned int) * 512 * (size_t)n), "cudaMalloc hist");
+    cu(cudaMalloc(&b->d_hist, sizeof(unsigned int) * pt::kModeScratch * (size_t)n), "cudaMalloc hist");
     cu(cudaMalloc(&b->d_pos, sizeof(int4) * n), "cudaMalloc pos");
     cu(cudaMalloc(&b->d_resp, sizeof(float) * n), "cudaMalloc resp");
     if (rc == PT_OK) {
@@ -470,7 +493,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
         cu(cudaMemcpy(b->d_taps_col, tcol.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
         cu(cudaMemset(b->d_keys, 0, sizeof(unsigned long long) * n), "memset");
         cu(cudaMemset(b->d_counters, 0, sizeof(unsigned int) * 3 * n), "memset");
-        cu(cudaMemset(b->d_hist, 0, sizeof(unsigned int) * 512 * (size_t)n), "memset");
+        cu(cudaMemset(b->d_hist, 0, sizeof(unsigned int) * pt::kModeScratch * (size_t)n), "memset");
         cu(cudaMemset(b->d_pos, 0, sizeof(int4) * n), "memset");
         cu(cudaMemset(b->d_resp, 0, sizeof(float) * n), "memset");
     }
@@ -577,10 +600,13 @@ int pt_batch_set_fill(pt_batch *b, const int *fills)
 int pt_batch_set_guess(pt_batch *b, const int32_t *guess_ij)
 {
     if (!b || !guess_ij) return fail(PT_ERR_ARG, "NULL argument");
-    int rc = set_device(b);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(b->stream));
-    return upload_guess(b, guess_ij, b->stream);
+    // Kept in the host mirror; the device copy is refreshed (flush_guess) by the next call that steps on the
+    // device.  The per-frame host path (footprint streaming of pageable frames) never needs it there.
+    b->h_guess.assign(guess_ij, guess_ij + 2 * (size_t)b->n);
+    b->h_guess_valid = true;
+    b->d_guess_stale = true;
+    b->guess_set = true;
+    return PT_OK;
 }
 
 int pt_batch_step(pt_batch *b, const int32_t *guess_ij, int32_t *out_ij, int32_t *out_raw_ij, float *out_resp)
@@ -594,11 +620,17 @@ int pt_batch_step(pt_batch *b, const int32_t *guess_ij, int32_t *out_ij, int32_t
     if (rc) return rc;
     if (guess_ij) { rc = upload_guess(b, guess_ij, b->stream); if (rc) return rc; }
     else if (!b->guess_set) return fail(PT_ERR_STATE, "no guess on the device: pass guess_ij or call pt_batch_set_guess");
+    else { rc = flush_guess(b); if (rc) return rc; }
     pt::WinArgs a = make_args(b, base, stride, pitch, b->H, b->W, b->d_guess, b->n);
     a.next_guess = b->d_guess;
     rc = launch_step(b, a, b->n, b->stream);
     if (rc) return rc;
-    if (out_ij || out_raw_ij || out_resp) return read_results(b, out_ij, out_raw_ij, out_resp, b->stream);
+    b->h_guess_valid = false;
+    if (out_ij || out_raw_ij || out_resp) {
+        rc = read_results(b, out_ij, out_raw_ij, out_resp, b->stream);
+        if (rc == PT_OK) mirror_from_results(b, out_ij);
+        return rc;
+    }
     return PT_OK;
 }
 
@@ -615,6 +647,8 @@ int pt_batch_track_device_async(pt_batch *b, const void *dev_base, size_t step_s
     rc = b->d_traj_pos.ensure(sizeof(int4) * (size_t)b->n * T); if (rc) return rc;
     rc = b->d_traj_resp.ensure(sizeof(float) * (size_t)b->n * T); if (rc) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : b->stream;
+    rc = flush_guess(b, s); if (rc) return rc;
+    b->h_guess_valid = false;                 // the chain advances on the device only
     const size_t es = px_size(b->pixel);
     {
         // the specialised kernel chains all T steps inside one launch (one CTA per video)
@@ -736,11 +770,9 @@ void lane_worker(HostTrack *ht, pt_lane *ln)
             pt::WinArgs a = make_args(b, ln->d_crops.p, crop_elems, cp, fr, fc, b->d_center + ln->v0, nl);
             a.fill = b->d_fill + ln->v0;
             a.keys = b->d_keys + ln->v0; a.counters = b->d_counters + ln->v0; a.tickets = b->d_counters + b->n + 2 * ln->v0;
-            a.out_pos = b->d_pos + ln->v0; a.out_resp = b->d_resp + ln->v0;
+            a.out_pos = hres; a.out_resp = hresp;      // pinned + mapped: the kernel stores the results straight into host memory
             e = launch_windows(b, a, nl, ln->stream);
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(hres, b->d_pos + ln->v0, sizeof(int4) * nl, cudaMemcpyDeviceToHost, ln->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(hresp, b->d_resp + ln->v0, sizeof(float) * nl, cudaMemcpyDeviceToHost, ln->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ln->stream);
         if (e != cudaSuccess) {
             int expected = PT_OK;
@@ -785,8 +817,11 @@ int ensure_lanes(pt_batch *b)
         rc = ln.d_crops.ensure(cp * fr * es * nl); if (rc) return rc;
         rc = ln.h_res.ensure(nl * 20); if (rc) return rc;
     }
-    std::vector<int2> c(b->n, make_int2(b->rr + b->w + 1, b->rc + b->w + 1));
-    CU(cudaMemcpy(b->d_center, c.data(), sizeof(int2) * (size_t)b->n, cudaMemcpyHostToDevice));
+    if (b->center_key[0] != b->rr || b->center_key[1] != b->rc || b->center_key[2] != b->w) {
+        std::vector<int2> c(b->n, make_int2(b->rr + b->w + 1, b->rc + b->w + 1));
+        CU(cudaMemcpy(b->d_center, c.data(), sizeof(int2) * (size_t)b->n, cudaMemcpyHostToDevice));
+        b->center_key[0] = b->rr; b->center_key[1] = b->rc; b->center_key[2] = b->w;
+    }
     return PT_OK;
 }
 
@@ -811,6 +846,7 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
         // whole frames: upload step t+1 on the copy stream into the other slot
         // while step t's kernel runs; one D2H of the result per step.
         b->bound_base = nullptr;
+        rc = flush_guess(b); if (rc) return rc;
         CU(cudaStreamSynchronize(b->stream));
         rc = upload_frames(b, frames, pitch, 0, b->copy_stream); if (rc) return rc;
         CU(cudaEventRecord(b->ev_done[0], b->copy_stream));
@@ -830,6 +866,7 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
         }
         b->cur_slot = (T - 1) & 1;
         b->have_frames = true;
+        mirror_from_results(b, out_ij + (size_t)(T - 1) * n * 2);
         return PT_OK;
     }
 
@@ -868,6 +905,7 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
             rc = b->h_traj.ensure(cnt * 20); if (rc) return rc;
             int4 *hpos = (int4 *)b->h_traj.p;
             float *hresp = (float *)((char *)b->h_traj.p + cnt * 16);
+            rc = flush_guess(b); if (rc) return rc;
             CU(cudaMemcpyAsync(b->d_ptrs.p, hp, cnt * sizeof(void *), cudaMemcpyHostToDevice, b->stream));
             pt::WinArgs a = make_args(b, nullptr, 0, pitch, b->H, b->W, b->d_guess, b->n);
             a.frame_ptrs = (const void *const *)b->d_ptrs.p;
@@ -877,6 +915,7 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
             rc = launch_step(b, a, b->n, b->stream); if (rc) return rc;
             CU(cudaStreamSynchronize(b->stream));
             for (size_t i = 0; i < cnt; ++i) { out_ij[2 * i] = hpos[i].x; out_ij[2 * i + 1] = hpos[i].y; if (out_resp) out_resp[i] = hresp[i]; }
+            mirror_from_results(b, out_ij + (size_t)(T - 1) * n * 2);
             return PT_OK;
         }
     }
@@ -886,17 +925,24 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
     rc = ensure_lanes(b); if (rc) return rc;
     HostTrack ht;
     ht.b = b; ht.frames = frames; ht.T = T; ht.pitch = pitch; ht.out_ij = out_ij; ht.out_resp = out_resp;
-    ht.guess.resize(n * 2);
-    CU(cudaStreamSynchronize(b->stream));
-    CU(cudaMemcpy(ht.guess.data(), b->d_guess, sizeof(int2) * n, cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(b->stream));          // fill values / centres / earlier steps are complete
+    b->staging_busy = false;
+    if (b->h_guess_valid) ht.guess = b->h_guess;
+    else {
+        ht.guess.resize(n * 2);
+        CU(cudaMemcpy(ht.guess.data(), b->d_guess, sizeof(int2) * n, cudaMemcpyDeviceToHost));
+    }
     std::vector<std::thread> th;
     for (size_t i = 1; i < b->lanes.size(); ++i) th.emplace_back(lane_worker, &ht, &b->lanes[i]);
     lane_worker(&ht, &b->lanes[0]);
     for (auto &t : th) t.join();
     b->launches += (long long)T * (long long)b->lanes.size();
     if (ht.err.load() != PT_OK) return fail(ht.err.load(), "footprint streaming failed: %s", ht.err_msg.c_str());
-    // leave the chain state on the device, as pt_batch_step would
-    CU(cudaMemcpy(b->d_guess, ht.guess.data(), sizeof(int2) * n, cudaMemcpyHostToDevice));
+    // the chain state now lives in the host mirror; the device copy is refreshed lazily (flush_guess)
+    // by the next call that steps on the device, as pt_batch_step would expect
+    b->h_guess = ht.guess;
+    b->h_guess_valid = true;
+    b->d_guess_stale = true;
     return PT_OK;
 }
 

@@ -327,11 +327,21 @@ cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s)
 }
 
 // ---------------------------------------------------------------------------
-// mode(frame): 256-bin histogram + position of each value's last occurrence in
-// column-major order.  StatsBase.mode returns the value whose count first
-// reaches the final maximum while scanning; a value reaches its final count at
-// its LAST occurrence, so among the values tied for the maximum count the one
-// whose last occurrence comes earliest wins.  (src/PawsomeTracker.jl:47)
+// mode(frame) — fillvalue = mode(_img), src/PawsomeTracker.jl:47.
+// StatsBase.mode returns the value whose count first reaches the final maximum while scanning in
+// column-major order; a value reaches its final count at its LAST occurrence, so among the values
+// tied for the maximum count the one whose last occurrence comes earliest wins.
+//
+// Fast path (one pass at HBM speed): counts only.  mode_count_kernel reads 16-byte vectors and
+// accumulates into a shared histogram with one private column per LANE (hist[bin][lane]: the 32 lanes
+// of a warp always hit 32 different banks, whatever the pixel values — a flat background does not
+// serialise), merging runs of equal pixels inside a vector first.  mode_decide_kernel picks the
+// maximum; only if two or more values tie for it (rare) does the slow pass run: mode_hist_kernel
+// also records every value's last column-major position and mode_pick_kernel applies the tie rule.
+// Both slow kernels are always enqueued and return at once for videos without a tie, so the host
+// never has to look at the counts.
+// Scratch `hist`: [n][kModeScratch] unsigned, zero between calls: 0..255 counts + 256..511 last
+// positions (slow pass), 512..767 counts (fast pass), 768 tie flag.
 // ---------------------------------------------------------------------------
 constexpr int kModeSplit = 16;   // CTAs per frame
 constexpr int kModeThreads = 256;
@@ -343,14 +353,124 @@ template <> __device__ __forceinline__ int px_bin<float>(const float *p)
     int b = __float2int_rn(__ldg(p) * 255.0f);
     return min(max(b, 0), 255);
 }
+__device__ __forceinline__ int f32_bin(float x)
+{
+    int b = __float2int_rn(x * 255.0f);
+    return min(max(b, 0), 255);
+}
 
 template <typename PixT>
 __global__ void __launch_bounds__(kModeThreads)
-mode_hist_kernel(const void *frames, size_t frame_stride, int pitch, int H, int W, unsigned int *hist)
+mode_count_kernel(const void *frames, size_t frame_stride, int pitch, int H, int W, unsigned int *hist)
+{
+    constexpr int PXV = 16 / (int)sizeof(PixT);            // pixels per 16-byte vector
+    __shared__ unsigned int s_cnt[256 * 32];               // [bin][lane]
+    const int v = blockIdx.y, lane = threadIdx.x & 31;
+    const PixT *frame = reinterpret_cast<const PixT *>(frames) + (size_t)v * frame_stride;
+    for (int i = threadIdx.x; i < 256 * 32; i += kModeThreads) s_cnt[i] = 0u;
+    __syncthreads();
+    const int rows_per = (H + gridDim.x - 1) / gridDim.x;
+    const int y0 = blockIdx.x * rows_per, y1 = min(H, y0 + rows_per);
+    const int vec_per_row = (W + PXV - 1) / PXV;
+    const int total = (y1 - y0) * vec_per_row;
+    unsigned int *col = s_cnt + lane;
+    auto count_vec = [&](const uint4 &q, int nvalid) {
+        if (sizeof(PixT) == 1) {
+            const unsigned int wd[4] = {q.x, q.y, q.z, q.w};
+            int run_bin = (int)(wd[0] & 0xFFu), run = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int bin = (int)((wd[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+                if (k < nvalid) {
+                    if (bin == run_bin) ++run;
+                    else { atomicAdd(col + run_bin * 32, (unsigned int)run); run_bin = bin; run = 1; }
+                }
+            }
+            if (run) atomicAdd(col + run_bin * 32, (unsigned int)run);
+        } else {
+            const float fv[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nvalid) atomicAdd(col + f32_bin(fv[k]) * 32, 1u);
+        }
+    };
+    // four independent 16-byte loads in flight per thread before the first is consumed
+    constexpr int U = 4;
+    for (int e0 = threadIdx.x; e0 < total; e0 += U * kModeThreads) {
+        uint4 q[U];
+        int nv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * kModeThreads;
+            nv[u] = 0;
+            q[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (e < total) {
+                const int r = e / vec_per_row, c = e - r * vec_per_row;
+                q[u] = __ldg(reinterpret_cast<const uint4 *>(frame + (size_t)(y0 + r) * pitch) + c);
+                nv[u] = min(PXV, W - c * PXV);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (nv[u] > 0) count_vec(q[u], nv[u]);
+    }
+    __syncthreads();
+    // thread t sums bin t over the 32 lane columns (rotated start: conflict-free)
+    unsigned int sum = 0u;
+    const int t = threadIdx.x;
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) sum += s_cnt[t * 32 + ((c + t) & 31)];
+    if (sum) atomicAdd(hist + (size_t)v * kModeScratch + 512 + t, sum);
+}
+
+// One CTA of 256 threads per video: maximum count; unique → publish the fill, else raise the tie flag.
+__global__ void __launch_bounds__(256)
+mode_decide_kernel(unsigned int *hist, int pixel, float *fill_out, int *fill_int_out)
+{
+    __shared__ unsigned long long s_key[8];
+    __shared__ unsigned int s_ties[8];
+    const int v = blockIdx.x, i = threadIdx.x;
+    unsigned int *h = hist + (size_t)v * kModeScratch;
+    const unsigned int cnt = h[512 + i];
+    unsigned long long key = ((unsigned long long)cnt << 8) | (unsigned long long)i;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+        key = o > key ? o : key;
+    }
+    if ((i & 31) == 0) s_key[i >> 5] = key;
+    __syncthreads();
+    unsigned long long k = s_key[0];
+#pragma unroll
+    for (int t = 1; t < 8; ++t) k = s_key[t] > k ? s_key[t] : k;
+    const unsigned int maxc = (unsigned int)(k >> 8);
+    const unsigned int tied = __popc(__ballot_sync(0xFFFFFFFFu, cnt == maxc));
+    if ((i & 31) == 0) s_ties[i >> 5] = tied;
+    __syncthreads();
+    unsigned int nt = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) nt += s_ties[t];
+    if (i == 0) {
+        if (nt == 1) {
+            const int bin = (int)(k & 0xFFull);
+            fill_int_out[v] = bin;
+            fill_out[v] = pixel == 0 ? (float)bin : (float)bin / 255.0f;
+            h[768] = 0u;
+        } else {
+            h[768] = 1u;      // tie for the maximum count: the slow pass decides by last positions
+        }
+    }
+    h[512 + i] = 0u;          // leave the scratch zeroed for the next call
+}
+
+template <typename PixT>
+__global__ void __launch_bounds__(kModeThreads)
+mode_hist_kernel(const void *frames, size_t frame_stride, int pitch, int H, int W, unsigned int *hist, int only_ties)
 {
     __shared__ unsigned int s_cnt[256];
     __shared__ unsigned int s_last[256];
     const int v = blockIdx.y;
+    if (only_ties && hist[(size_t)v * kModeScratch + 768] == 0u) return;
     const PixT *frame = reinterpret_cast<const PixT *>(frames) + (size_t)v * frame_stride;
     for (int i = threadIdx.x; i < 256; i += kModeThreads) { s_cnt[i] = 0u; s_last[i] = 0u; }
     __syncthreads();
@@ -381,18 +501,19 @@ mode_hist_kernel(const void *frames, size_t frame_stride, int pitch, int H, int 
         }
     }
     __syncthreads();
-    unsigned int *h = hist + (size_t)v * 512;
+    unsigned int *h = hist + (size_t)v * kModeScratch;
     for (int i = threadIdx.x; i < 256; i += kModeThreads) {
         if (s_cnt[i]) { atomicAdd(h + i, s_cnt[i]); atomicMax(h + 256 + i, s_last[i]); }
     }
 }
 
 __global__ void __launch_bounds__(256)
-mode_pick_kernel(unsigned int *hist, int pixel, float *fill_out, int *fill_int_out)
+mode_pick_kernel(unsigned int *hist, int pixel, float *fill_out, int *fill_int_out, int only_ties)
 {
     __shared__ unsigned long long s_key[8];
     const int v = blockIdx.x, i = threadIdx.x;
-    unsigned int *h = hist + (size_t)v * 512;
+    unsigned int *h = hist + (size_t)v * kModeScratch;
+    if (only_ties && h[768] == 0u) return;
     const unsigned int cnt = h[i], last = h[256 + i];
     // larger count wins; ties → smaller last position
     unsigned long long key = ((unsigned long long)cnt << 40) | ((unsigned long long)(0xFFFFFFFFu - last) << 8) | (unsigned long long)i;
@@ -413,6 +534,7 @@ mode_pick_kernel(unsigned int *hist, int pixel, float *fill_out, int *fill_int_o
     }
     __syncthreads();
     h[i] = 0u; h[256 + i] = 0u; // leave the scratch zeroed for the next call
+    if (i == 0) h[768] = 0u;
 }
 
 cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int H, int W, int n,
@@ -420,13 +542,27 @@ cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int 
                         cudaStream_t s)
 {
     dim3 grid(kModeSplit, (unsigned)n);
+    const size_t es = pixel == 0 ? 1 : 4;
+    // the vector path needs 16-byte aligned rows that can be read up to the next multiple of 16 bytes
+    const bool vec = !getenv("PT_MODE_SLOW") && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 && ((size_t)pitch * es) % 16 == 0 &&
+                     (frame_stride * es) % 16 == 0 && (size_t)pitch * es >= (((size_t)W * es + 15) & ~(size_t)15);
+    cudaError_t e;
+    if (vec) {
+        if (pixel == 0) mode_count_kernel<uint8_t><<<grid, kModeThreads, 0, s>>>(frames, frame_stride, pitch, H, W, hist);
+        else mode_count_kernel<float><<<grid, kModeThreads, 0, s>>>(frames, frame_stride, pitch, H, W, hist);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        mode_decide_kernel<<<n, 256, 0, s>>>(hist, pixel, fill_out, fill_int_out);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     if (pixel == 0)
-        mode_hist_kernel<uint8_t><<<grid, kModeThreads, 0, s>>>(frames, frame_stride, pitch, H, W, hist);
+        mode_hist_kernel<uint8_t><<<grid, kModeThreads, 0, s>>>(frames, frame_stride, pitch, H, W, hist, vec ? 1 : 0);
     else
-        mode_hist_kernel<float><<<grid, kModeThreads, 0, s>>>(frames, frame_stride, pitch, H, W, hist);
-    cudaError_t e = cudaGetLastError();
+        mode_hist_kernel<float><<<grid, kModeThreads, 0, s>>>(frames, frame_stride, pitch, H, W, hist, vec ? 1 : 0);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    mode_pick_kernel<<<n, 256, 0, s>>>(hist, pixel, fill_out, fill_int_out);
+    mode_pick_kernel<<<n, 256, 0, s>>>(hist, pixel, fill_out, fill_int_out, vec ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -109,7 +109,8 @@ cudaError_t launch_window45_quad(const WinArgs &a, int n, cudaStream_t s);
 const char *window45_quad_name();
 
 // fillvalue = mode(frame) (src/PawsomeTracker.jl:47) for n frames.
-// hist: [n][512] unsigned scratch (counts, last positions), zeroed by the launch.
+// hist: [n][kModeScratch] unsigned scratch, zero before the first call and left zeroed by every call.
+constexpr int kModeScratch = 832;
 cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int H, int W, int n,
                         int pixel, unsigned int *hist, float *fill_out, int *fill_int_out,
                         cudaStream_t s);

@@ -258,13 +258,23 @@ class Tracker:
         self._batch.set_frames([self.img])
         self.fillvalue = int(self._batch.compute_fill()[0])
         self.last_response = float("nan")
+        self._call = None
 
     def __call__(self, guess):
-        # a tracker is a batch of one: footprint streaming of the current host frame
-        self._batch.set_guess([[int(guess[0]), int(guess[1])]])
-        out, resp = self._batch.track_host([[self.img]], mode="footprint")
-        self.last_response = float(resp[0, 0])
-        return (int(out[0, 0, 0]), int(out[0, 0, 1]))
+        # a tracker is a batch of one: footprint streaming of the current host frame.  This is the per-frame
+        # call of the reference's loop (:167), so the ctypes argument buffers are built once and reused.
+        c = self._call
+        if c is None:
+            pitch = _check_frame(self.img, self.sz[0], self.sz[1], self._batch.pixel)
+            c = self._call = ((C.c_int32 * 2)(), (C.c_void_p * 1)(self.img.ctypes.data), pitch,
+                              (C.c_int32 * 2)(), (C.c_float * 1)())
+        g, ptrs, pitch, out, resp = c
+        g[0], g[1] = int(guess[0]), int(guess[1])
+        h = self._batch._h
+        check(lib.pt_batch_set_guess(h, g))
+        check(lib.pt_batch_track_host(h, ptrs, 1, pitch, 0, out, resp))
+        self.last_response = float(resp[0])
+        return (out[0], out[1])
 
     def step_resident(self, guess):
         """Same result with the whole frame uploaded to HBM first (the

@@ -178,6 +178,37 @@ def test_mode_kernel_tie_rule(gpu_pkg, oracle):
             b.close()
 
 
+@pytest.mark.parametrize("slow", [False, True])
+def test_mode_fast_and_slow_paths(gpu_pkg, oracle, monkeypatch, slow):
+    """mode(frame): the counting pass (vector loads, lane-private histogram columns) decides alone unless two
+    values tie for the maximum count; then — and with PT_MODE_SLOW always — the last-position pass applies
+    StatsBase's rule.  Frame widths that are not multiples of 16, u8 and f32 pixels, several frames per batch."""
+    if slow:
+        monkeypatch.setenv("PT_MODE_SLOW", "1")
+    rng = np.random.default_rng(8)
+    for (H, W) in [(37, 53), (64, 64), (120, 200), (9, 1000)]:
+        frames = [rng.integers(0, 256, (H, W)).astype(np.uint8),                       # noise: near-ties likely
+                  rng.integers(100, 104, (H, W)).astype(np.uint8),                     # four values
+                  np.full((H, W), 7, np.uint8)]                                        # flat
+        tie = np.zeros((H, W), np.uint8); tie[:, : W // 2] = 9; tie[:, W // 2: 2 * (W // 2)] = 200
+        frames.append(tie)                                                             # exact tie (plus zeros if W odd)
+        b = gpu_pkg.TrackerBatch(len(frames), (H, W), 10, (21, 21), True)
+        try:
+            b.set_frames(frames)
+            got = b.compute_fill()
+            assert [int(x) for x in got] == [oracle.mode(f) for f in frames], (H, W)
+            assert [int(x) for x in b.compute_fill()] == [int(x) for x in got]         # scratch left clean
+        finally:
+            b.close()
+        f32 = [(f.astype(np.float32) / np.float32(255.0)) for f in frames]
+        b = gpu_pkg.TrackerBatch(len(frames), (H, W), 10, (21, 21), True, dtype=np.float32)
+        try:
+            b.set_frames(f32)
+            assert [int(x) for x in b.compute_fill()] == [oracle.mode(f) for f in frames], (H, W)
+        finally:
+            b.close()
+
+
 def test_blank_window_is_a_documented_near_tie(gpu_pkg, oracle):
     """A window that sees only the fill value has a flat response: the oracle's
     maximum is decided by 1e-17-level rounding noise, the GPU's (exactly zero)
