@@ -181,14 +181,15 @@ def _no_diagnostics(diagnostic_file):
 
 
 def track(file, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, target_width=25, start_location=None,
-          window_size=None, darker_target=True, fps=24, diagnostic_file=None, device=0):
+          window_size=None, darker_target=True, fps=24, diagnostic_file=None, device=0, parallel=False):
     """`track(file; …)` (src/PawsomeTracker.jl:130-146) or, when `file` is a list,
     the segmented `track(files; …)` (:181-214).  Returns (ts, ij) with ij an
-    (n, 2) array of 1-based (row, col)."""
+    (n, 2) array of 1-based (row, col).  `parallel` (lists only): see track_segments."""
     if isinstance(file, (list, tuple)):
         return track_segments(file, start=start, stop=stop, target_width=target_width,
                               start_location=start_location, window_size=window_size,
-                              darker_target=darker_target, fps=fps, diagnostic_file=diagnostic_file, device=device)
+                              darker_target=darker_target, fps=fps, diagnostic_file=diagnostic_file, device=device,
+                              parallel=parallel)
     _no_diagnostics(diagnostic_file)
     if window_size is None:
         window_size = guess_window_size(target_width)
@@ -197,17 +198,19 @@ def track(file, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, target_width=25, 
 
 
 def track_segments(files: Sequence, *, start=None, stop=None, target_width=25, start_location=None,
-                   window_size=None, darker_target=True, fps=24, diagnostic_file=None, device=0):
-    """`track(files::AbstractVector; …)` — src/PawsomeTracker.jl:181-214."""
+                   window_size=None, darker_target=True, fps=24, diagnostic_file=None, device=0,
+                   parallel: bool = False):
+    """`track(files::AbstractVector; …)` — src/PawsomeTracker.jl:181-214.
+
+    parallel=True (no equivalent in the reference): a segment that comes with its own
+    `start_location` does not depend on the segment before it (`coalesce`, :204), so the file list splits into
+    independent CHAINS of segments; the chains advance concurrently as the videos of one TrackerBatch.  The
+    result is identical to the serial loop."""
     _no_diagnostics(diagnostic_file)
-    nfiles = len(files)
-    start = [0.0] * nfiles if start is None or np.isscalar(start) and start == 0 else list(start)
-    stop = ([DEFAULT_MAX_DURATION_SECONDS] * nfiles
-            if stop is None or np.isscalar(stop) and stop == DEFAULT_MAX_DURATION_SECONDS else list(stop))
-    start_location = [None] * nfiles if start_location is None else list(start_location)
-    if not (nfiles == len(start) == len(stop) == len(start_location)):            # @assert (:193)
-        raise AssertionError(f"Array length mismatch: files={nfiles}, start={len(start)}, stop={len(stop)}, "
-                             f"start_location={len(start_location)}")
+    if parallel:
+        return _track_segments_parallel(files, start, stop, target_width, start_location, window_size,
+                                        darker_target, fps, device)
+    start, stop, start_location = _segment_args(files, start, stop, start_location)
     if window_size is None:
         window_size = guess_window_size(target_width)
     window_size = fix_window_size(window_size)
@@ -222,6 +225,145 @@ def track_segments(files: Sequence, *, start=None, stop=None, target_width=25, s
     n = sum(len(t) for t in tss)
     step = (tss[0][1] - tss[0][0]) if len(tss[0]) > 1 else 0.0
     ts = tss[0][0] + step * np.arange(n)                                          # range(first, step=…, length=n) (:210)
+    return ts, np.concatenate(ijs, axis=0)
+
+
+def _segment_args(files, start, stop, start_location):
+    nfiles = len(files)
+    start = [0.0] * nfiles if start is None or np.isscalar(start) and start == 0 else list(start)
+    stop = ([DEFAULT_MAX_DURATION_SECONDS] * nfiles
+            if stop is None or np.isscalar(stop) and stop == DEFAULT_MAX_DURATION_SECONDS else list(stop))
+    start_location = [None] * nfiles if start_location is None else list(start_location)
+    if not (nfiles == len(start) == len(stop) == len(start_location)):            # @assert (:193)
+        raise AssertionError(f"Array length mismatch: files={nfiles}, start={len(start)}, stop={len(stop)}, "
+                             f"start_location={len(start_location)}")
+    return start, stop, start_location
+
+
+class _Chain:
+    """Consecutive segments linked by `coalesce(loc, end_location)` (:204): only the first has its own start."""
+
+    def __init__(self, segs, fps):
+        self.segs = segs                      # [(file index, file, t_start, t_stop, loc)]
+        self.fps = fps
+        self.k = -1                           # current segment
+        self.vid = None
+        self.n = 0
+        self.count = 0
+        self.out = {}                         # file index -> list of (i, j)
+        self.last = None                      # previous result (chain state)
+        self.done = False
+        self.placeholder = None               # last frame seen: stands in once the chain is exhausted
+        self._open_next()
+
+    def _open_next(self):
+        self.k += 1
+        if self.k >= len(self.segs):
+            self.done = True
+            return
+        idx, f, t0, t1, loc = self.segs[self.k]
+        t = t1 - t0
+        self.n = int(round(self.fps * t))
+        self.vid = _Resampled(open_video(f), t0, t, self.fps)
+        self.count = 0
+        self.out[idx] = []
+
+    def next_frame(self):
+        """(frame, is_first_frame_of_segment) or None when the chain is exhausted."""
+        while not self.done:
+            first = self.count == 0
+            if (first or self.count < self.n) and not self.vid.eof():      # read(vid) :159, loop condition :162
+                return self.vid.read(), first
+            self._open_next()
+        return None
+
+    def record(self, ij):
+        idx = self.segs[self.k][0]
+        self.out[idx].append((int(ij[0]), int(ij[1])))
+        self.last = (int(ij[0]), int(ij[1]))
+        self.count += 1
+
+
+def _track_segments_parallel(files, start, stop, target_width, start_location, window_size, darker_target, fps, device):
+    start, stop, start_location = _segment_args(files, start, stop, start_location)
+    if window_size is None:
+        window_size = guess_window_size(target_width)
+    window_size = fix_window_size(window_size)
+    # split into chains: a segment with its own start_location starts a new chain
+    groups = []
+    for i, (f, t0, t1, loc) in enumerate(zip(files, start, stop, start_location)):
+        if i == 0 or loc is not None:
+            groups.append([])
+        groups[-1].append((i, f, t0, t1, loc))
+    chains = [_Chain(g, fps) for g in groups]
+    nc = len(chains)
+    cur = [c.next_frame() for c in chains]
+    if any(x is None for x in cur):
+        raise EOFError("a segment chain has no frame")
+    shapes = {x[0].shape for x in cur}
+    if len(shapes) != 1:
+        raise ValueError("parallel segment tracking needs segments of one frame size")
+    H, W = cur[0][0].shape
+    batch = TrackerBatch(nc, (H, W), target_width, window_size, darker_target, dtype=cur[0][0].dtype, device=device)
+    fills = np.zeros(nc, np.int32)
+    try:
+        while True:
+            active = [x is not None for x in cur]
+            if not any(active):
+                break
+            # finished chains keep their last frame as a placeholder; their results are ignored
+            frames = []
+            for v, x in enumerate(cur):
+                if x is not None:
+                    frames.append(x[0])
+                else:
+                    frames.append(chains[v].placeholder)
+            new_seg = [x is not None and x[1] for x in cur]
+            if any(new_seg):
+                # a new Tracker per segment: fill = mode of the segment's first frame (:47, :94)
+                batch.set_frames(frames)
+                f_all = batch.compute_fill()
+                for v in range(nc):
+                    if new_seg[v]:
+                        fills[v] = f_all[v]
+                batch.set_fill(fills)
+            guess = np.zeros((nc, 2), np.int32)
+            auto = [False] * nc
+            for v, c in enumerate(chains):
+                if cur[v] is None:
+                    guess[v] = c.last if c.last is not None else (1, 1)
+                elif new_seg[v]:
+                    loc = c.segs[c.k][4]
+                    loc = loc if loc is not None else (CartesianIndex(*c.last) if c.last is not None else None)   # coalesce (:204)
+                    guess[v] = get_guess(loc, c.vid.vid, cur[v][0])
+                    auto[v] = loc is None
+                else:
+                    guess[v] = c.last
+            if any(auto):
+                # start_location = missing on the very first segment: auto-detect window size .÷ 4 (:99-105)
+                batch.set_window((H // 4, W // 4))
+                out_a, _ = batch.step(guess)
+                batch.set_window(window_size)
+            batch.set_guess(guess)
+            out, _ = batch.track_host([frames], mode="footprint")
+            for v, c in enumerate(chains):
+                if cur[v] is None:
+                    continue
+                c.placeholder = frames[v]
+                c.record(out_a[v] if auto[v] else out[0, v])
+            cur = [c.next_frame() if x is not None else None for c, x in zip(chains, cur)]
+    finally:
+        batch.close()
+    tss, ijs = [], []
+    for i, (t0, t1) in enumerate(zip(start, stop)):
+        n = int(round(fps * (t1 - t0)))
+        ts_i = np.linspace(t0, t1, n)
+        rec = next(c.out[i] for c in chains if i in c.out)
+        tss.append(ts_i[:len(rec)])
+        ijs.append(np.asarray(rec, np.int64).reshape(len(rec), 2))
+    n = sum(len(t) for t in tss)
+    step = (tss[0][1] - tss[0][0]) if len(tss[0]) > 1 else 0.0
+    ts = tss[0][0] + step * np.arange(n)                                          # (:209-210)
     return ts, np.concatenate(ijs, axis=0)
 
 

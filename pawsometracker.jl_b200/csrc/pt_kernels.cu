@@ -193,28 +193,61 @@ dog_rect_argmax_generic(const WinArgs a)
         }
         __syncthreads();
 
-        // ---- row pass: lane = footprint row of the batch, warp = group of 8 output columns; one packed
-        // FFMA2 advances (narrow, wide) of an output together
+        // ---- row pass: lane = footprint row of the batch, warp = group of 8 output columns.  The factors are
+        // symmetric, so out = g0·x0 + Σ_d g_d·(x_-d + x_+d): one FADD feeds one packed FFMA2 that advances
+        // (narrow, wide) together — 3 issue slots per tap pair instead of 4.  Two register windows slide
+        // outwards from the centre (left one to the left, right one to the right), C taps per step; the
+        // last w mod C tap pairs are handled one at a time.  Same summation order as row_pass45.
         {
-            const float *src = s_in + lane * PIN + warp * R;
+            const float *ctr = s_in + lane * PIN + warp * R + w;      // x0 of output 0
             float2 acc[R];
-            float win[R + C - 1];
+            float lw[R + C - 1], rw[R + C - 1];
+            {
+                const float2 g0 = s_trow[w];
 #pragma unroll
-            for (int j = 0; j < R; ++j) acc[j] = make_float2(0.f, 0.f);
+                for (int j = 0; j < R; ++j) { const float x0 = ctr[j]; acc[j] = make_float2(x0 * g0.x, x0 * g0.y); }
+            }
 #pragma unroll
-            for (int j = 0; j < R - 1; ++j) win[j] = src[j];
+            for (int i = 0; i < R - 1; ++i) { lw[C + i] = ctr[i]; rw[i] = ctr[1 + i]; }
+            const int nfull = w / C;
+            int d0 = 0;
 #pragma unroll 1
-            for (int k0 = 0; k0 < Lpad; k0 += C) {
+            for (int ch = 0; ch < nfull; ++ch, d0 += C) {
+                // lw[i] = ctr[-d0-C+i], rw[i] = ctr[d0+1+i]
 #pragma unroll
-                for (int t = 0; t < C; ++t) win[R - 1 + t] = src[k0 + R - 1 + t];
+                for (int i = 0; i < C; ++i) { lw[i] = ctr[-d0 - C + i]; rw[R - 1 + i] = ctr[d0 + R + i]; }
 #pragma unroll
-                for (int t = 0; t < C; ++t) {
-                    const float2 g = s_trow[k0 + t];
+                for (int t = 1; t <= C; ++t) {
+                    const float2 g = s_trow[w + d0 + t];
 #pragma unroll
-                    for (int j = 0; j < R; ++j) acc[j] = ffma2(make_float2(win[j + t], win[j + t]), g, acc[j]);
+                    for (int j = 0; j < R; ++j) {
+                        const float sm = lw[j + C - t] + rw[j + t - 1];
+                        acc[j] = ffma2(make_float2(sm, sm), g, acc[j]);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < R - 1; ++j) win[j] = win[j + C];
+                for (int i = R - 2; i >= 0; --i) lw[C + i] = lw[i];
+#pragma unroll
+                for (int i = 0; i < R - 1; ++i) rw[i] = rw[i + C];
+            }
+#pragma unroll 1
+            for (; d0 < w; ++d0) {
+                // one tap pair: d = d0+1; left values ctr[-d0-1+j], right values ctr[d0+1+j]
+                const float nl = ctr[-d0 - 1], nr = ctr[d0 + R];
+                const float2 g = s_trow[w + d0 + 1];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const float left = (j == 0) ? nl : lw[C + j - 1];
+                    const float right = (j < R - 1) ? rw[j] : nr;
+                    const float sm = left + right;
+                    acc[j] = ffma2(make_float2(sm, sm), g, acc[j]);
+                }
+#pragma unroll
+                for (int i = R - 2; i >= 1; --i) lw[C + i] = lw[C + i - 1];
+                lw[C] = nl;
+#pragma unroll
+                for (int i = 0; i < R - 2; ++i) rw[i] = rw[i + 1];
+                rw[R - 2] = nr;
             }
             const int f = b * TB + lane;
             float2 *dst = s_ring + (size_t)(f % RING) * RP + warp * R;

@@ -507,6 +507,30 @@ def test_config5_segments_sar_start_fps(gpu_pkg, oracle):
     assert rmse < 1.5, rmse        # column quantisation by SAR=2 adds up to 1 px
 
 
+def test_segment_parallel_equals_serial(gpu_pkg):
+    """segments that bring their own start_location start independent chains which advance
+    concurrently in one batch; the result must equal the reference-order serial loop (:202-206), including
+    per-segment fills, the first-frame refinement, an auto-detected first segment and unequal segment lengths."""
+    H, W, fps = 240, 320, 24.0
+    _, tra = gpu_pkg.build_trajectory(0.8 * 120, fps, (120, 160), seconds=6.0, seed=5)
+    parts = gpu_pkg.my_partition(len(tra), 5)
+    segs = [gpu_pkg.SyntheticVideo(H, W, tra[a:b + 1], 25, True, fps=fps) for a, b in parts]
+    fr3 = np.stack([segs[3].frame(k) for k in range(len(segs[3]))])
+    fr3[fr3 == 128] = 140                                                  # another background: the fill differs per segment
+    segs[3] = gpu_pkg.ArrayVideo(fr3, fps=fps)
+    stops = [(b - a + 1) / fps for a, b in parts]
+    stops[1] = stops[1] * 0.5                                              # a shorter second segment
+    for first_loc in (gpu_pkg.CartesianIndex(120, 160), None):
+        locs = [first_loc, None, gpu_pkg.CartesianIndex(int(tra[parts[2][0], 0]), int(tra[parts[2][0], 1])), None,
+                (int(tra[parts[4][0], 1]), int(tra[parts[4][0], 0]))]      # three chains: [0,1] [2,3] [4]
+        kw = dict(start=[0.0] * 5, stop=stops, target_width=25, start_location=locs, darker_target=True, fps=fps)
+        ts_s, ij_s = gpu_pkg.track(segs, **kw)
+        ts_p, ij_p = gpu_pkg.track(segs, parallel=True, **kw)
+        np.testing.assert_array_equal(ij_p, ij_s)
+        np.testing.assert_array_equal(ts_p, ts_s)
+        assert len(ij_s) > 100
+
+
 def test_large_batch_1080p_properties(gpu_pkg):
     """BASELINE config 3 geometry at full size (256 × 1080p), size-independent checks:
     every video finds its disk centre; results do not depend on batch composition."""
