@@ -449,7 +449,7 @@ def test_track_autodetect_and_batch_api(gpu_pkg, oracle):
 
 def test_config2_1080p_autodetect_then_track(gpu_pkg, oracle):
     """BASELINE config 2 (shortened): one 1080p video, start_location = missing → auto-detect over the
-    271×481 window centred on the frame (tile kernel), then windowed tracking; positions identical to the
+    271×481 window centred on the frame (dog_rect45_march), then windowed tracking; positions identical to the
     oracle-driven loop and within 1 px RMS of the ground truth."""
     H, W, nfr = 1080, 1920, 60
     start = (540, 960)
