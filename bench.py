@@ -84,6 +84,7 @@ def render_ring_device(torch, pos, slots, device):
         for v in range(n):
             cy, cx = int(p[v, 0]) - 1, int(p[v, 1]) - 1
             ring[s, v, cy - r:cy + r + 1, cx - r:cx + r + 1][mask] = 0
+    torch.cuda.synchronize(device)      # torch renders on its own stream; the library launches on another one
     return ring
 
 

@@ -181,6 +181,8 @@ struct pt_batch {
     unsigned long long *d_keys = nullptr;
     unsigned int *d_counters = nullptr;
     unsigned int *d_hist = nullptr;
+    unsigned int *d_xflag = nullptr;     // [n] hand-off flags of the rotating-slot kernel (zero between launches)
+    int2 *d_xpos = nullptr;              // [n] hand-off guesses
     int4 *d_pos = nullptr;
     float *d_resp = nullptr;
     // own HBM frame store (two slots so a whole-frame upload can overlap a step)
@@ -234,6 +236,8 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     a.h_taps = b->h_taps.data();
     a.frame_ptrs = nullptr;
     a.xkeys = nullptr; a.xcnt = nullptr;
+    a.xflag = (nwin == b->n) ? b->d_xflag : nullptr;     // whole-batch launches only (one stream at a time)
+    a.xpos = b->d_xpos;
     (void)nwin;
     return a;
 }
@@ -487,6 +491,8 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     cu(cudaMalloc(&b->d_counters, sizeof(unsigned int) * 3 * n), "cudaMalloc counters");   // [n] completion + [n][2] ticket scratch
     cu(cudaMalloc(&b->d_hist, sizeof(unsigned int) * pt::kModeScratch * (size_t)n), "cudaMalloc hist");
     cu(cudaMalloc(&b->d_pos, sizeof(int4) * n), "cudaMalloc pos");
+    cu(cudaMalloc(&b->d_xflag, sizeof(unsigned int) * n), "cudaMalloc xflag");
+    cu(cudaMalloc(&b->d_xpos, sizeof(int2) * n), "cudaMalloc xpos");
     cu(cudaMalloc(&b->d_resp, sizeof(float) * n), "cudaMalloc resp");
     if (rc == PT_OK) {
         cu(cudaMemcpy(b->d_taps_row, trow.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
@@ -495,6 +501,8 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
         cu(cudaMemset(b->d_counters, 0, sizeof(unsigned int) * 3 * n), "memset");
         cu(cudaMemset(b->d_hist, 0, sizeof(unsigned int) * pt::kModeScratch * (size_t)n), "memset");
         cu(cudaMemset(b->d_pos, 0, sizeof(int4) * n), "memset");
+        cu(cudaMemset(b->d_xflag, 0, sizeof(unsigned int) * n), "memset");
+        cu(cudaMemset(b->d_xpos, 0, sizeof(int2) * n), "memset");
         cu(cudaMemset(b->d_resp, 0, sizeof(float) * n), "memset");
     }
     if (rc != PT_OK) { pt_batch_destroy(b); return rc; }
@@ -516,7 +524,7 @@ void pt_batch_destroy(pt_batch *b)
     }
     cudaFree(b->d_taps_row); cudaFree(b->d_taps_col); cudaFree(b->d_fill); cudaFree(b->d_fill_i);
     cudaFree(b->d_guess); cudaFree(b->d_center); cudaFree(b->d_keys); cudaFree(b->d_counters);
-    cudaFree(b->d_hist); cudaFree(b->d_pos); cudaFree(b->d_resp);
+    cudaFree(b->d_hist); cudaFree(b->d_pos); cudaFree(b->d_resp); cudaFree(b->d_xflag); cudaFree(b->d_xpos);
     for (int i = 0; i < 2; ++i) {
         b->d_frames[i].release(); b->h_stage[i].release();
         if (b->ev_copy[i]) cudaEventDestroy(b->ev_copy[i]);

@@ -45,6 +45,8 @@ struct WinArgs {
                                // used for zero-copy reads of pinned host frames (specialised kernel only)
     unsigned long long *xkeys; // [n][T] cross-CTA argmax keys   } exchange scratch of the 4-CTA-per-window kernel,
     unsigned int *xcnt;        // [n][T] arrival counters        } zeroed by the launcher's caller before each launch
+    unsigned int *xflag;       // [n] hand-off flags   } dog_window45_rot (windows hopping between SMs); zero between launches,
+    int2 *xpos;                // [n] hand-off guesses } the kernel leaves them zeroed
     const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
 };
 

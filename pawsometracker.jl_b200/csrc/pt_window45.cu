@@ -78,7 +78,9 @@ struct Args45 {
     int4 *out_pos; float *out_resp;     // [n] last step
     int2 *next_guess;                   // [n] or null
     int4 *traj_pos; float *traj_resp;   // [T][n] or null
-    int skew;                           // 1: alternate the row passes of the two windows of a CTA (token)
+    int skew;                           // 1: alternate the row passes of the two windows of a CTA (token); 2: lock
+    unsigned int *xflag;                // [n] hand-off flags of dog_window45_rot (zero between launches)
+    int2 *xpos;                         // [n] hand-off guesses
     long long *dbg;                     // optional [n][T][6]: smid|globaltimer, clock64 at start / stage / row / col / end
 };
 
@@ -327,7 +329,11 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
     const int firstB = (int)blockIdx.x + (int)gridDim.x;
     const int cntB = (firstB < a.n) ? (a.n - 1 - firstB) / stride + 1 : 0;
     const int NA = cntA * a.T, NB = cntB * a.T;
-    const bool tokens = a.skew != 0 && NB > 0;
+    const bool tokens = a.skew == 1 && NB > 0;
+    const bool locked = a.skew == 2 && NB > 0;     // row passes mutually exclusive through a lock in shared memory
+    __shared__ int s_rowlock;
+    if (threadIdx.x == 0) s_rowlock = 0;
+    __syncthreads();
     int round = 0;
 
   for (int v = (int)blockIdx.x + (int)gridDim.x * half; v < a.n; v += stride) {
@@ -373,6 +379,9 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
                 }
             }
         }
+        if (locked && tid == 0) {
+            while (atomicCAS(&s_rowlock, 0, 1) != 0) __nanosleep(40);
+        }
         bar_half(half);
         if (dbg && tid == 0) dbg[2] = clock64();
         if (tokens) {                                          // wait for the row-pass token
@@ -382,6 +391,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
 
         row_pass45(s_in, s_mid, tid, tp);
         bar_half(half);
+        if (locked && tid == 0) atomicExch(&s_rowlock, 0);
         if (tokens) {                                          // hand the row-pass token to the other window
             if (half == 0) { if (round < NB) asm volatile("bar.arrive 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
             else           { if (round + 1 < NA) asm volatile("bar.arrive 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
@@ -426,6 +436,161 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// dog_window45_rot — the same per-window work as dog_window45_argmax for batches of S < n < 2·S windows
+// (S = #SMs; BASELINE config 3: 256 windows on 148 SMs).  There a static split gives 2S − n SMs one window
+// (11.5 K cycles per frame) and the other SMs two (18.6 K each, which sets the launch time) while the
+// single-window SMs idle 40 % of the time.  Here the "holes" ROTATE: the 2S window slots (slot σ = SM σ mod S,
+// half σ div S) form a ring that holds the n windows in a fixed cyclic order, and the arc of nh = 2S − n empty
+// slots advances by its own length every time step, i.e. the nh windows just ahead of the arc hop back over it
+// (closed form: rot_window()).  Every window therefore has its SM to itself for nh/n of its steps and all
+// windows finish together instead of the lone ones early.  A hop is a hand-off through global memory (guess +
+// release flag; the receiving slot is empty and polls), nh of n windows per step; the L2 prefetch issued by the
+// old SM serves the new one (L2 is shared).  The row passes of the two halves of an SM exclude each other
+// through a lock in shared memory (same effect as the token of dog_window45_argmax, but a half never waits for
+// a partner that is empty or late).  All CTAs must be co-resident (cooperative launch).
+// ---------------------------------------------------------------------------------------------------
+// window held by slot `slot` of a ring of R slots at step t (m windows, nh = R − m empty slots), or −1
+__device__ __forceinline__ int rot_window(int slot, int t, int R, int m, int nh)
+{
+    const int a0 = (nh * t) % R;
+    int k = slot - a0;
+    if (k < 0) k += R;
+    if (k >= m) return -1;                   // empty slot at this step
+    int u = (nh * t) % m + k;
+    if (u >= m) u -= m;
+    return u;
+}
+
+template <typename PixT>
+__global__ void __launch_bounds__(CTA_THREADS, 1)
+dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps45 tp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long s_keys[2][2 * NWARPS];
+    __shared__ int s_rowlock;
+    __shared__ int2 s_handoff[2];
+
+    const int pw = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = (pw >> 2) & 1;
+    const int warp = (((pw & 3) + 2 * half) & 3) + 4 * (pw >> 3);
+    const int tid = warp * 32 + lane;
+    float *s_in = reinterpret_cast<float *>(smem_raw + half * HALF_SMEM);
+    float2 *s_mid = reinterpret_cast<float2 *>(s_in + FR * PIN + 1);
+    unsigned long long *s_key = s_keys[half];
+    const int R = 2 * (int)gridDim.x, m = a.n, nh = R - m, slot = (int)blockIdx.x + (int)gridDim.x * half;
+    if (threadIdx.x == 0) s_rowlock = 0;
+    __syncthreads();
+
+    int prev_v = -1;
+    int2 g = make_int2(0, 0);
+    float fill = 0.f;
+    for (int t = 0; t < a.T; ++t) {
+        const unsigned int it = (unsigned int)t;
+        const int v = rot_window(slot, t, R, m, nh);
+        if (v < 0) { prev_v = -1; continue; }
+        if (v != prev_v) {
+            fill = a.fill[v];
+            if (t == 0) {
+                g = a.guess[v];
+            } else {
+                // the window hops in from another SM: wait for its previous step (acquire), take the guess, clear the flag
+                if (tid == 0) {
+                    unsigned int f;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.xflag + v) : "memory");
+                        if (f != (unsigned int)t) __nanosleep(100);
+                    } while (f != (unsigned int)t);
+                    s_handoff[half] = a.xpos[v];
+                    a.xflag[v] = 0u;
+                }
+                bar_half(half);
+                g = s_handoff[half];
+            }
+            prev_v = v;
+        }
+        long long *dbg = a.dbg ? a.dbg + ((size_t)v * a.T + t) * 6 : nullptr;
+        if (dbg && tid == 0) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            dbg[0] = ((long long)gt << 8) | (long long)(smid & 0xFF);
+            dbg[1] = clock64();
+        }
+        const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)t * a.step_stride + (size_t)v * a.frame_stride;
+        const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);
+        const int fy0 = wy0 - HW, fx0 = wx0 - HW;
+
+        stage_tile<PixT>(frame, a.pitch, a.H, a.W, fy0, fx0, fill, s_in, warp, lane);
+
+        if (t + 1 < a.T) {                                       // warm L2 with everything the next step can touch
+            const PixT *nframe = frame + a.step_stride;
+            constexpr int PR = FR + WR - 1;
+            constexpr int NLMAX = (int)(((FC + WC) * sizeof(PixT) + 127) / 128) + 1;
+            const int py0 = fy0 - WR / 2, pxb = (fx0 - WC / 2) * (int)sizeof(PixT);
+            const int line0 = pxb >> 7;
+            const int nl = ((pxb + (FC + WC - 1) * (int)sizeof(PixT) - 1) >> 7) - line0 + 1;
+            const int rowbytes = a.W * (int)sizeof(PixT);
+            for (int e = tid; e < PR * NLMAX; e += THREADS) {
+                const int r = e / NLMAX, ln = e - r * NLMAX;
+                const int Y = py0 + r;
+                const int off = (line0 + ln) << 7;
+                if (ln < nl && Y >= 0 && Y < a.H && off >= 0 && off < rowbytes) {
+                    const char *ptr = reinterpret_cast<const char *>(nframe + (size_t)Y * a.pitch) + off;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                }
+            }
+        }
+        if (tid == 0) {
+            while (atomicCAS(&s_rowlock, 0, 1) != 0) __nanosleep(40);
+        }
+        bar_half(half);
+        if (dbg && tid == 0) dbg[2] = clock64();
+
+        row_pass45(s_in, s_mid, tid, tp);
+        bar_half(half);
+        if (tid == 0) atomicExch(&s_rowlock, 0);
+        if (dbg && tid == 0) dbg[3] = clock64();
+
+        unsigned long long key = col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+            key = o > key ? o : key;
+        }
+        if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
+        bar_half(half);
+        if (dbg && tid == 0) dbg[4] = clock64();
+        {
+            const unsigned long long *kk = s_key + (it & 1) * NWARPS;
+            unsigned long long k = kk[0];
+#pragma unroll
+            for (int i = 1; i < NWARPS; ++i) k = kk[i] > k ? kk[i] : k;
+            const unsigned int idx = key_index(k);
+            const int xx = (int)(idx / WR), yy = (int)(idx - xx * WR);
+            const int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;
+            const int ci = min(max(raw_i, 1), a.H), cj = min(max(raw_j, 1), a.W);
+            if (tid == 0) {
+                const float resp = key_value(k);
+                const int4 p = make_int4(ci, cj, raw_i, raw_j);
+                if (a.traj_pos) { a.traj_pos[(size_t)t * a.n + v] = p; a.traj_resp[(size_t)t * a.n + v] = resp; }
+                if (t == a.T - 1) {
+                    a.out_pos[v] = p; a.out_resp[v] = resp;
+                    if (a.next_guess) a.next_guess[v] = make_int2(ci, cj);
+                } else if (rot_window(slot, t + 1, R, m, nh) != v) {
+                    // the window hops to another SM for the next step: publish the guess, then the flag (release)
+                    a.xpos[v] = make_int2(ci, cj);
+                    const unsigned int f = (unsigned int)(t + 1);
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.xflag + v), "r"(f) : "memory");
+                }
+                if (dbg) dbg[5] = clock64();
+            }
+            g = make_int2(ci, cj);
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Large rectangles at l = 65 (auto-detect window size .÷ 4, src/PawsomeTracker.jl:99-105; the full-frame
@@ -649,6 +814,21 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
     // one CTA per SM, two windows per CTA; with n ≤ #SMs every window gets its own SM
     const int grid = std::min(sms, n);
     const size_t smem = 2 * HALF_SMEM;
+    // S < n < 2S with few empty slots (at most n/4: every step nh windows hop), frames in HBM, more than one
+    // step: rotate the empty slots (dog_window45_rot)
+    const char *rot_env = getenv("PT_W45_ROT");
+    const int rot_on = rot_env ? atoi(rot_env) : 1;
+    k.xflag = a.xflag; k.xpos = a.xpos;
+    if (rot_on && k.xflag && k.xpos && !k.frame_ptrs && k.T > 1 && n > sms && n < 2 * sms && 4 * (2 * sms - n) <= n) {
+        void *params[2] = {(void *)&k, (void *)&tp};
+        if (pixel == 0) {
+            { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_rot<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
+            return cudaLaunchCooperativeKernel((const void *)dog_window45_rot<uint8_t>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
+        } else {
+            { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_rot<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
+            return cudaLaunchCooperativeKernel((const void *)dog_window45_rot<float>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
+        }
+    }
     if (pixel == 0) {
         { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_argmax<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
         dog_window45_argmax<uint8_t><<<grid, CTA_THREADS, smem, s>>>(k, tp);

@@ -546,6 +546,7 @@ def test_large_batch_1080p_properties(gpu_pkg):
         for v in range(n):
             cy, cx = int(centres[t, v, 0]) - 1, int(centres[t, v, 1]) - 1
             dev[t, v, cy - 12:cy + 13, cx - 12:cx + 13][mask] = 0
+    torch.cuda.synchronize()          # torch renders on its own stream; the batch launches on another one
     with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
         b.bind_device_frames(dev.data_ptr(), H * W, W)
         assert (b.compute_fill() == 128).all()
@@ -554,6 +555,7 @@ def test_large_batch_1080p_properties(gpu_pkg):
         np.testing.assert_array_equal(ij, centres)
         # permutation invariance: same videos in reverse order
         rev = dev.flip(1).contiguous()
+        torch.cuda.synchronize()
         b.set_guess(ij[0][::-1].copy())
         ij2, resp2 = b.track_device(rev.data_ptr(), n * H * W, H * W, W, T)
         np.testing.assert_array_equal(ij2[:, ::-1], ij)
@@ -561,10 +563,12 @@ def test_large_batch_1080p_properties(gpu_pkg):
     assert np.all(resp > 0.08)
 
 
-@pytest.mark.parametrize("n,T", [(1, 1), (3, 5), (149, 4), (300, 3), (700, 2)])
+@pytest.mark.parametrize("n,T", [(1, 1), (3, 5), (149, 4), (300, 3), (700, 2), (256, 9), (240, 7), (295, 5)])
 def test_batch_sizes_exercise_cta_video_loop(gpu_pkg, oracle, n, T):
     """dog_window45_argmax hosts two videos per CTA and loops `v += 2·#CTAs`: cover one video, an odd
-    count just above the SM count (lone second halves), and more videos than one wave holds.  Every
+    count just above the SM count (lone second halves), and more videos than one wave holds; with
+    1.6·#SMs <= n < 2·#SMs and T > 1 the chained call runs dog_window45_rot (windows hop between SMs while
+    the empty slots rotate), which must agree with the per-step launches step by step.  Every
     video has its own frame content; spot-check a sample of videos against the oracle loop, all of them
     against ground truth, and the per-step path against the chained one."""
     import torch
@@ -603,6 +607,34 @@ def test_batch_sizes_exercise_cta_video_loop(gpu_pkg, oracle, n, T):
     # disks that are fully inside the frame are found exactly at their centre
     inside = (cent[..., 0] > 13) & (cent[..., 0] < H - 13) & (cent[..., 1] > 13) & (cent[..., 1] < W - 13)
     np.testing.assert_array_equal(ij[inside], cent[inside])
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_rotating_slots_equal_static_split(gpu_pkg, monkeypatch, dtype):
+    """dog_window45_rot vs dog_window45_argmax on the same 240-video, 11-step chain: identical positions AND
+    bit-identical responses (same arithmetic, only the SM a window runs on changes); hand-off scratch left clean
+    (a second chained call gives the same answer)."""
+    import torch
+    n, T, H, W = 240, 11, 96, 128
+    rng = np.random.default_rng(77)
+    base = rng.integers(0, 256, (T, n, H, W)).astype(np.uint8)          # noise: every response value is informative
+    frames = base if dtype is np.uint8 else base.astype(np.float32) / np.float32(255.0)
+    dev = torch.from_numpy(frames).cuda()
+    start = np.stack([rng.integers(1, H + 1, n), rng.integers(1, W + 1, n)], axis=-1)
+    with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True, dtype=dtype) as b:
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        b.compute_fill()
+        b.set_guess(start)
+        ij_rot, r_rot = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        b.set_guess(start)
+        ij_rot2, r_rot2 = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        monkeypatch.setenv("PT_W45_ROT", "0")
+        b.set_guess(start)
+        ij_st, r_st = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+    np.testing.assert_array_equal(ij_rot, ij_st)
+    np.testing.assert_array_equal(r_rot, r_st)
+    np.testing.assert_array_equal(ij_rot2, ij_st)
+    np.testing.assert_array_equal(r_rot2, r_st)
 
 
 def test_float32_frames_chained_and_batched(gpu_pkg, oracle):
