@@ -353,6 +353,7 @@ def run_gpu(args, ranks):
                 run_chain(Wm % slots, K)                                             # EXACTLY K timed steps
                 e1.record()
             timed_launches = batch.launch_count - lc0
+            batch_kernel = batch.last_kernel or batch_kernel
             torch.cuda.synchronize(device)
             ranks.barrier()
             reps_ms.append(ranks.max_over_ranks(e0.elapsed_time(e1), device))        # max over ranks, device time
@@ -458,7 +459,7 @@ def run_gpu(args, ranks):
     t_roof = max(flops_launch / (fp32_peak * 1e12), bytes_launch / (hbm_peak * 1e9))
     # DRAM traffic of this kernel from profiles/r01_window45_final_ncu_full_selected.csv (one `ncu --set full`
     # capture of a 20-step launch: dram read 209.1 MB + write 5.0 MB): 10.70 MB per 256-video step
-    traffic_per_step = 10.70e6 if batch_kernel == "dog_window45_argmax" else None
+    traffic_per_step = 10.70e6 if batch_kernel in ("dog_window45_argmax", "dog_window45_rot") else None
     roofline = {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach_tflops / fp32_peak,
                 "traffic": traffic_per_step * steps_per_launch if traffic_per_step else None,
@@ -596,8 +597,9 @@ def run_gpu(args, ranks):
                 "cpu_baseline": cpu, "fullframe_dog": fullframe, "balanced_batch": balanced, "mode_fill": mode_fill,
                 "gpu_launches": int(timed_launches),
                 "gpu_launches_note": f"{batch_kernel} chains the K steps of the timed region inside "
-                                     f"{int(timed_launches)} launch(es) (one CTA per SM hosts two videos; the serial "
-                                     "frame chain of a video never leaves its CTA)",
+                                     f"{int(timed_launches)} launch(es) (one CTA per SM hosts two videos; with "
+                                     "dog_window45_rot the empty window slots rotate over the SMs and a video "
+                                     "hops to another SM every n/(2S-n) steps, its guess handed over through global memory)",
                 "gpu_launches_e2e": int(launches_e2e),
                 "positions_correct": bool(all_ok),
                 "ms_K_repeats": {"min": float(np.min(reps_ms)), "median": ms_K, "max": float(np.max(reps_ms))}}

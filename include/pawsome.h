@@ -170,6 +170,9 @@ PT_API int pt_batch_read_track(pt_batch *b, int T, int32_t *out_ij, float *out_r
  * the name of the window kernel variant the current geometry dispatches to. */
 PT_API long long pt_batch_launch_count(const pt_batch *b);
 PT_API const char *pt_batch_kernel_name(const pt_batch *b);
+/* Name of the kernel the batch's most recent step/track launch actually ran ("" before the first one):
+ * e.g. a chained pt_batch_track_device over 256 videos runs dog_window45_rot, a single step dog_window45_argmax. */
+PT_API const char *pt_batch_last_kernel(const pt_batch *b);
 PT_API void *pt_batch_stream(const pt_batch *b); /* the cudaStream_t the batch launches on */
 
 /* ---- single tracker (thin wrapper over a batch of one) -------------------- */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pt_batch_read_track": (C.c_int, [_vp, C.c_int, _i32p, _fp]),
     "pt_batch_launch_count": (C.c_longlong, [_vp]),
     "pt_batch_kernel_name": (C.c_char_p, [_vp]),
+    "pt_batch_last_kernel": (C.c_char_p, [_vp]),
     "pt_batch_stream": (_vp, [_vp]),
     "pt_tracker_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(_vp)]),

@@ -199,6 +199,7 @@ struct pt_batch {
     PinnedBuf h_stage[2], h_out;
     std::vector<pt_lane> lanes;
     long long launches = 0;
+    const char *last_kernel = "";        // name of the kernel the most recent launch_step ran
     bool use45 = false;
 };
 
@@ -292,7 +293,15 @@ int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
             done = true;
         }
     }
-    if (!done) e = launch_windows(b, a, nwin, s);
+    if (!done) {
+        e = launch_windows(b, a, nwin, s);
+        if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
+            b->last_kernel = pt::window45_uses_rot(a, nwin) ? pt::window45_rot_name() : pt::window45_name();
+        else if (b->use45 && pt::rect45_supported(a, b->pixel)) b->last_kernel = pt::rect45_name();
+        else b->last_kernel = b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
+    } else {
+        b->last_kernel = pt::window45_quad_name();
+    }
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     b->launches += 1;
     return PT_OK;
@@ -1050,6 +1059,8 @@ const char *pt_batch_kernel_name(const pt_batch *b)
     if (b->use45 && a.L == 65 && !getenv("PT_DISABLE_RECT45") && (long long)a.wr * a.wc >= 24 * 24) return pt::rect45_name();
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
 }
+
+const char *pt_batch_last_kernel(const pt_batch *b) { return b ? b->last_kernel : ""; }
 
 void *pt_batch_stream(const pt_batch *b) { return b ? (void *)b->stream : nullptr; }
 

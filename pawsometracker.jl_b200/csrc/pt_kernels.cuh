@@ -96,6 +96,8 @@ cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s);
 bool window45_supported(const WinArgs &a, int pixel);
 cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s);
 const char *window45_name();
+bool window45_uses_rot(const WinArgs &a, int n);   // launch_window45 would run dog_window45_rot for this launch
+const char *window45_rot_name();
 void window45_set_debug(long long *dev_buf);
 long long *window45_debug_ptr();   // phase-timestamp buffer [n][T][6] (profiling aid), nullptr = off
 

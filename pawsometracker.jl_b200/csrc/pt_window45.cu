@@ -498,10 +498,12 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
                 // the window hops in from another SM: wait for its previous step (acquire), take the guess, clear the flag
                 if (tid == 0) {
                     unsigned int f;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.xflag + v) : "memory");
-                        if (f != (unsigned int)t) __nanosleep(100);
-                    } while (f != (unsigned int)t);
+                    for (;;) {                 // poll relaxed (no L1 invalidation per poll), then one acquire
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.xflag + v) : "memory");
+                        if (f == (unsigned int)t) break;
+                        __nanosleep(32);
+                    }
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.xflag + v) : "memory");
                     s_handoff[half] = a.xpos[v];
                     a.xflag[v] = 0u;
                 }
@@ -784,6 +786,30 @@ static void fold_taps(const WinArgs &a, Taps45 &tp)
     }
 }
 
+static int sm_count()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, vsm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&vsm, cudaDevAttrMultiProcessorCount, dev);
+        sms = vsm > 0 ? vsm : 148;
+    }
+    return sms;
+}
+
+// S < n < 2S with few empty slots (at most n/4: every step nh windows hop), frames in HBM, more than one
+// step: rotate the empty slots (dog_window45_rot)
+bool window45_uses_rot(const WinArgs &a, int n)
+{
+    const char *rot_env = getenv("PT_W45_ROT");
+    const int rot_on = rot_env ? atoi(rot_env) : 1;
+    const int sms = sm_count();
+    return rot_on && a.xflag && a.xpos && !a.frame_ptrs && a.T > 1 && n > sms && n < 2 * sms && 4 * (2 * sms - n) <= n;
+}
+
+const char *window45_rot_name() { return "dog_window45_rot"; }
+
 cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
 {
     if (!a.h_taps) return cudaErrorInvalidValue;
@@ -804,22 +830,12 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
         if (skew < 0) { const char *e2 = getenv("PT_W45_SKEW"); skew = e2 ? atoi(e2) : 1; }
         k.skew = skew;
     }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, vsm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&vsm, cudaDevAttrMultiProcessorCount, dev);
-        sms = vsm > 0 ? vsm : 148;
-    }
+    const int sms = sm_count();
     // one CTA per SM, two windows per CTA; with n ≤ #SMs every window gets its own SM
     const int grid = std::min(sms, n);
     const size_t smem = 2 * HALF_SMEM;
-    // S < n < 2S with few empty slots (at most n/4: every step nh windows hop), frames in HBM, more than one
-    // step: rotate the empty slots (dog_window45_rot)
-    const char *rot_env = getenv("PT_W45_ROT");
-    const int rot_on = rot_env ? atoi(rot_env) : 1;
     k.xflag = a.xflag; k.xpos = a.xpos;
-    if (rot_on && k.xflag && k.xpos && !k.frame_ptrs && k.T > 1 && n > sms && n < 2 * sms && 4 * (2 * sms - n) <= n) {
+    if (window45_uses_rot(a, n)) {
         void *params[2] = {(void *)&k, (void *)&tp};
         if (pixel == 0) {
             { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_rot<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }

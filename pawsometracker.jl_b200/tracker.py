@@ -233,6 +233,11 @@ class TrackerBatch:
         return lib.pt_batch_kernel_name(self._h).decode()
 
     @property
+    def last_kernel(self) -> str:
+        """Kernel the most recent step / track launch ran."""
+        return lib.pt_batch_last_kernel(self._h).decode()
+
+    @property
     def stream(self) -> int:
         return lib.pt_batch_stream(self._h) or 0
 
