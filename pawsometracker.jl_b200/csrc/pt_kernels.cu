@@ -368,7 +368,7 @@ cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s)
 // Fast path (one pass at HBM speed): counts only.  mode_count_kernel reads 16-byte vectors and
 // accumulates into a shared histogram with one private column per LANE (hist[bin][lane]: the 32 lanes
 // of a warp always hit 32 different banks, whatever the pixel values — a flat background does not
-// serialise), merging runs of equal pixels inside a vector first.  mode_decide_kernel picks the
+// serialise); uniform vectors / words cost a single atomic.  mode_decide_kernel picks the
 // maximum; only if two or more values tie for it (rare) does the slow pass run: mode_hist_kernel
 // also records every value's last column-major position and mode_pick_kernel applies the tie rule.
 // Both slow kernels are always enqueued and return at once for videos without a tie, so the host
@@ -409,17 +409,26 @@ mode_count_kernel(const void *frames, size_t frame_stride, int pitch, int H, int
     unsigned int *col = s_cnt + lane;
     auto count_vec = [&](const uint4 &q, int nvalid) {
         if (sizeof(PixT) == 1) {
-            const unsigned int wd[4] = {q.x, q.y, q.z, q.w};
-            int run_bin = (int)(wd[0] & 0xFFu), run = 0;
+            // whole vector one value (flat background): one atomic; else word by word: a uniform word costs one
+            // atomic, a mixed one four (no run bookkeeping: per pixel that costs more issue slots than it saves)
+            const unsigned int rep = __byte_perm(q.x, 0, 0);
+            if (nvalid == 16 && q.x == rep && q.y == rep && q.z == rep && q.w == rep) {
+                atomicAdd(col + (q.x & 0xFFu) * 32, 16u);
+            } else {
+                const unsigned int wd[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int bin = (int)((wd[k >> 2] >> (8 * (k & 3))) & 0xFFu);
-                if (k < nvalid) {
-                    if (bin == run_bin) ++run;
-                    else { atomicAdd(col + run_bin * 32, (unsigned int)run); run_bin = bin; run = 1; }
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned int w4 = wd[i];
+                    const int nv4 = nvalid - 4 * i;                       // valid pixels of this word
+                    if (nv4 >= 4 && w4 == __byte_perm(w4, 0, 0)) {
+                        atomicAdd(col + (w4 & 0xFFu) * 32, 4u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < nv4) atomicAdd(col + ((w4 >> (8 * k)) & 0xFFu) * 32, 1u);
+                    }
                 }
             }
-            if (run) atomicAdd(col + run_bin * 32, (unsigned int)run);
         } else {
             const float fv[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
 #pragma unroll

@@ -839,11 +839,15 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
         void *params[2] = {(void *)&k, (void *)&tp};
         if (pixel == 0) {
             { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_rot<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-            return cudaLaunchCooperativeKernel((const void *)dog_window45_rot<uint8_t>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
+            e = cudaLaunchCooperativeKernel((const void *)dog_window45_rot<uint8_t>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
         } else {
             { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_rot<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-            return cudaLaunchCooperativeKernel((const void *)dog_window45_rot<float>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
+            e = cudaLaunchCooperativeKernel((const void *)dog_window45_rot<float>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
         }
+        if (e == cudaSuccess) return e;
+        // the CTAs cannot all be co-resident right now (device shared with other work): the windows cannot hop
+        // safely — run the static split instead
+        cudaGetLastError();
     }
     if (pixel == 0) {
         { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_argmax<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }

@@ -1,5 +1,5 @@
 """Selected raw metrics of one `ncu --set full` capture → a small CSV for profiles/.
-Usage: ncu -i capture.ncu-rep --page raw --csv > raw.csv; python tools/ncu_select.py raw.csv > profiles/<name>.csv"""
+Usage: ncu -i capture.ncu-rep --page raw --csv > raw.csv; python tools/ncu_select.py raw.csv [launch index] > profiles/<name>.csv"""
 import csv, sys
 PREFIX = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct", "dram__throughput.avg.pct",
           "gpu__time_duration.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__block_size",
@@ -10,7 +10,7 @@ PREFIX = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput
           "smsp__average_warp_latency_issue_stalled", "smsp__average_warps_issue_stalled", "sm__sass_thread_inst_executed_op_f",
           "smsp__sass_thread_inst_executed_op_f", "sm__inst_executed.avg.per_cycle_active", "smsp__cycles_active.avg")
 rows = list(csv.reader(l for l in open(sys.argv[1]) if not l.startswith("==")))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units, vals = rows[0], rows[1], rows[2 + (int(sys.argv[2]) if len(sys.argv) > 2 else 0)]
 w = csv.writer(sys.stdout)
 w.writerow(["metric", "unit", "value"])
 w.writerow(["kernel", "", vals[hdr.index("Kernel Name")]])
