@@ -524,7 +524,9 @@ def run_gpu(args, ranks):
     ff = algorithmic_per_window(65, H, W)
     ff_t = float(np.min(ff_ms)) * 1e-3
     ffb_t = float(np.median(ffb_ms)) * 1e-3 / NFF                   # seconds per frame
-    fullframe = {"megapixels_per_s": H * W / ffb_t / 1e6, "us_per_frame": ffb_t * 1e6, "frames_per_launch": NFF,
+    ff_rate_all = ranks.sum_over_ranks(H * W / ffb_t / 1e6, device)           # every rank runs the same shape on its own GPU
+    fullframe = {"megapixels_per_s": ff_rate_all, "megapixels_per_s_per_gpu": H * W / ffb_t / 1e6, "n_gpus": world,
+                 "us_per_frame": ffb_t * 1e6, "frames_per_launch": NFF,
                  "launches_timed": ff_launches, "kernel": ff_kernel, "correct": fullframe_ok,
                  "achieved_tflops": ff["flops"] / ffb_t / 1e12, "frac_fp32": ff["flops"] / ffb_t / 1e12 / fp32_peak,
                  "algorithmic_flops_per_frame": ff["flops"],
