@@ -164,16 +164,22 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
         cok[k] = col[k] >= 0 && col[k] < FC;
     }
     unsigned int wd[RPW];
-    const uint8_t *base = frame + (size_t)(fy0 + warp) * pitch + X;      // only dereferenced when valid
+    // one running row pointer (bumped by NWARPS rows per load): two integer instructions per load instead of a
+    // fresh 64-bit row-times-pitch product
+    const uint8_t *rowp = frame + ((long long)(fy0 + warp) * pitch + X);   // only dereferenced when valid
+    const long long rstep = (long long)NWARPS * pitch;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
         const int Y = fy0 + f;
         const bool ok = wordok && (f < NROWS) && (kInterior || ((Y >= 0) && (Y < H)));
         wd[r] = fillw;
-        if (ok) wd[r] = __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)(r * NWARPS) * pitch));
+        if (ok) wd[r] = __ldg(reinterpret_cast<const unsigned int *>(rowp));
+        rowp += rstep;
     }
     const float cst = 8388608.0f + fill;
+    unsigned int magic;                                     // 2^23 exponent pattern kept in a register so that the
+    asm("mov.b32 %0, 0x4B000000;" : "=r"(magic));           // PRMT selectors are immediates (no selector MOVs)
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
@@ -183,7 +189,7 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
             float *dst = s_in + f * PIN;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float val = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + k)) - cst;
+                const float val = __uint_as_float(__byte_perm(w, magic, 0x7540 + k)) - cst;
                 if (cok[k]) dst[col[k]] = val;
             }
         }
@@ -369,13 +375,14 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             const int line0 = pxb >> 7;
             const int nl = ((pxb + (FC + WC - 1) * (int)sizeof(PixT) - 1) >> 7) - line0 + 1;   // exact: 2 or 3 for u8
             const int rowbytes = a.W * (int)sizeof(PixT);
-            for (int e = tid; e < PR * NLMAX; e += THREADS) {
-                const int r = e / NLMAX, ln = e - r * NLMAX;
-                const int Y = py0 + r;
-                const int off = (line0 + ln) << 7;
-                if (ln < nl && Y >= 0 && Y < a.H && off >= 0 && off < rowbytes) {
-                    const char *ptr = reinterpret_cast<const char *>(nframe + (size_t)Y * a.pitch) + off;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            static_assert(PR <= THREADS, "one thread per prefetched row");
+            const int Y = py0 + tid;                              // thread = row: its 2-3 lines share one address
+            if (tid < PR && Y >= 0 && Y < a.H) {
+                const char *ptr = reinterpret_cast<const char *>(nframe + (size_t)Y * a.pitch) + (line0 << 7);
+#pragma unroll
+                for (int ln = 0; ln < NLMAX; ++ln) {
+                    const int off = (line0 + ln) << 7;
+                    if (ln < nl && off >= 0 && off < rowbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (ln << 7)));
                 }
             }
         }
@@ -535,13 +542,14 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
             const int line0 = pxb >> 7;
             const int nl = ((pxb + (FC + WC - 1) * (int)sizeof(PixT) - 1) >> 7) - line0 + 1;
             const int rowbytes = a.W * (int)sizeof(PixT);
-            for (int e = tid; e < PR * NLMAX; e += THREADS) {
-                const int r = e / NLMAX, ln = e - r * NLMAX;
-                const int Y = py0 + r;
-                const int off = (line0 + ln) << 7;
-                if (ln < nl && Y >= 0 && Y < a.H && off >= 0 && off < rowbytes) {
-                    const char *ptr = reinterpret_cast<const char *>(nframe + (size_t)Y * a.pitch) + off;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            static_assert(PR <= THREADS, "one thread per prefetched row");
+            const int Y = py0 + tid;                              // thread = row: its 2-3 lines share one address
+            if (tid < PR && Y >= 0 && Y < a.H) {
+                const char *ptr = reinterpret_cast<const char *>(nframe + (size_t)Y * a.pitch) + (line0 << 7);
+#pragma unroll
+                for (int ln = 0; ln < NLMAX; ++ln) {
+                    const int off = (line0 + ln) << 7;
+                    if (ln < nl && off >= 0 && off < rowbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (ln << 7)));
                 }
             }
         }
