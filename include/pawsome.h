@@ -208,6 +208,13 @@ PT_API int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int 
 PT_API int pt_batch_rect_argmax_all(pt_batch *b, int y0, int x0, int wr, int wc,
                              int32_t *out_ij, float *out_resp, int no_readback);
 
+/* ---- page-locked host memory for decoders -------------------------------------- */
+/* A frame the decoder writes straight into page-locked memory (the destination of
+ * `read!(vid, trckr.img.data)`, src/PawsomeTracker.jl:166) can be read by the kernels over PCIe without a
+ * staging copy: pt_batch_track_host recognises such frames and runs the whole frame loop as one launch. */
+PT_API int pt_host_alloc(size_t bytes, void **out);
+PT_API int pt_host_free(void *p);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------- */
 /* FP32 FMA throughput of `device` in TFLOP/s (2 flops per FMA): packed=0 plain
  * FFMA, packed=1 fma.rn.f32x2.  The measured denominator of the FP32 roofline. */

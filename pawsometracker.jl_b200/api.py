@@ -16,6 +16,7 @@ from typing import NamedTuple, Sequence
 
 import numpy as np
 
+from .feeder import FrameFeeder
 from .tracker import Tracker, TrackerBatch, fix_window_size, guess_window_size
 
 DEFAULT_MAX_DURATION_SECONDS = 86399.999  # src/PawsomeTracker.jl:19
@@ -369,12 +370,13 @@ def _track_segments_parallel(files, start, stop, target_width, start_location, w
 
 def track_batch(files: Sequence, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, target_width=25,
                 start_location=None, window_size=None, darker_target=True, fps=24, device=0,
-                chunk_steps: int = 32):
+                chunk_steps: int | None = None, decode_workers: int | None = None):
     """Batched counterpart with no equivalent in the reference: `track` over
     many independent videos of identical geometry advanced in lock-step, one
     CTA group per (video, window) per launch.  Per-video results are identical
     to calling `track` on each video.  start_location: None, one location, or
-    one per video."""
+    one per video.  The videos are decoded concurrently by `decode_workers` host threads into a ring of
+    page-locked step-chunks (feeder.FrameFeeder) that the kernels read without a staging copy."""
     nv = len(files)
     if window_size is None:
         window_size = guess_window_size(target_width)
@@ -403,18 +405,19 @@ def track_batch(files: Sequence, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, 
             ij0[~missing] = out[~missing]
         batch.set_guess(ij0)
         out_all = [ij0[None]]
-        count = 1
-        while count < n and not any(v.eof() for v in vids):
-            steps = []
-            for _ in range(min(chunk_steps, n - count)):
-                if any(v.eof() for v in vids):
-                    break
-                steps.append([v.read() for v in vids])
-            if not steps:
-                break
-            ij, _ = batch.track_host(steps, mode="footprint")
-            out_all.append(ij)
-            count += len(steps)
+        if n > 1:
+            # decode threads fill a ring of page-locked step-chunks while the GPU tracks the previous chunk
+            # (zero-copy footprint reads, the chained kernel: one launch per chunk)
+            feeder = FrameFeeder(vids, (H, W), first[0].dtype, n - 1, chunk_steps=chunk_steps, workers=decode_workers)
+            try:
+                fs = H * W * first[0].dtype.itemsize
+                for chunk, Tk in feeder:
+                    base = chunk.ctypes.data
+                    ptrs = [base + (t * nv + v) * fs for t in range(Tk) for v in range(nv)]
+                    ij, _ = batch.track_host_ptrs(ptrs, Tk, W, "footprint")
+                    out_all.append(ij)
+            finally:
+                feeder.close()
         ij = np.concatenate(out_all, axis=0).astype(np.int64)  # (T, nv, 2)
     finally:
         batch.close()

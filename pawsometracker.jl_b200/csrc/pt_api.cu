@@ -1060,6 +1060,20 @@ const char *pt_batch_kernel_name(const pt_batch *b)
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
 }
 
+int pt_host_alloc(size_t bytes, void **out)
+{
+    if (!out || bytes == 0) return fail(PT_ERR_ARG, "bad argument");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return PT_OK;
+}
+
+int pt_host_free(void *p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return PT_OK;
+}
+
 const char *pt_batch_last_kernel(const pt_batch *b) { return b ? b->last_kernel : ""; }
 
 void *pt_batch_stream(const pt_batch *b) { return b ? (void *)b->stream : nullptr; }

@@ -698,6 +698,38 @@ def test_host_decode_feeder_cv2(gpu_pkg, tmp_path):
     assert np.abs(ij2[0] - tra[0]).max() <= 1
 
 
+def test_decode_feeder_pinned_ring_batch(gpu_pkg, tmp_path):
+    """several encoded files decoded concurrently by host threads into the ring of page-locked
+    step-chunks (FrameFeeder) and tracked in one batch with zero-copy footprint reads; decoding is deterministic, so
+    the batch must reproduce the per-file `track` exactly — including a file that is shorter than the others."""
+    cv2 = pytest.importorskip("cv2")
+    H, W, nfr = 240, 320, 40
+    paths, tras = [], []
+    for s_ in range(5):
+        tra = gpu_pkg.spiral(0.8 * 120, 600, (120, 160), seed=20 + s_)[:nfr - (7 if s_ == 3 else 0)]
+        vid = gpu_pkg.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+        path = str(tmp_path / f"clip{s_}.avi")
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 24.0, (W, H), isColor=True)
+        if not wr.isOpened():
+            pytest.skip("OpenCV cannot write MJPG/AVI in this build")
+        for k in range(len(tra)):
+            wr.write(cv2.cvtColor(vid.frame(k), cv2.COLOR_GRAY2BGR))
+        wr.release()
+        paths.append(path); tras.append(tra)
+    kw = dict(stop=nfr / 24.0, target_width=25, start_location=gpu_pkg.CartesianIndex(120, 160), fps=24)
+    ts, ij = gpu_pkg.track_batch(paths, chunk_steps=6, decode_workers=3, **kw)
+    assert ij.shape == (nfr - 7, 5, 2)                       # the batch stops with its shortest video (:162)
+    for v, path in enumerate(paths):
+        _, single = gpu_pkg.track(path, **kw)
+        np.testing.assert_array_equal(ij[:, v], single[:nfr - 7])
+        assert np.sqrt(np.mean(np.sum((ij[:, v] - tras[v][:nfr - 7]) ** 2, axis=1))) < 1.0
+    # the pinned buffer type on its own
+    pa = gpu_pkg.PinnedArray((3, 4, 5), np.uint8)
+    pa.array[...] = 7
+    assert pa.array.sum() == 7 * 60
+    pa.close()
+
+
 def test_plain_c_consumer_of_the_abi(gpu_pkg, oracle, tmp_path):
     """A C program compiled against include/pawsome.h and linked to libpawsome_cuda.so (no Python, no torch):
     the drop-in boundary as a foreign binding sees it."""
