@@ -208,6 +208,12 @@ PT_API int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int 
 PT_API int pt_batch_rect_argmax_all(pt_batch *b, int y0, int x0, int wr, int wc,
                              int32_t *out_ij, float *out_resp, int no_readback);
 
+/* ---- diagnostics (src/diagnose.jl) --------------------------------------------- */
+/* `imresize!(dia.buffer, img)` (src/diagnose.jl:33; buffer 360x640, :2) for the CURRENT frame in HBM of every
+ * video: bilinear, pixel-centre aligned, rounded to u8.  out: HOST memory, n*out_h*out_w bytes.  The overlay
+ * (label, dot, trail) and the encoder stay on the host. */
+PT_API int pt_batch_downscale(pt_batch *b, int out_h, int out_w, uint8_t *out);
+
 /* ---- page-locked host memory for decoders -------------------------------------- */
 /* A frame the decoder writes straight into page-locked memory (the destination of
  * `read!(vid, trckr.img.data)`, src/PawsomeTracker.jl:166) can be read by the kernels over PCIe without a

@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     ArrayVideo,
     CartesianIndex,
     CvVideo,
+    Diagnose,
     get_guess,
     get_start_ij_and_tracker,
     track,

@@ -64,6 +64,7 @@ SIGNATURES = {
     "pt_batch_launch_count": (C.c_longlong, [_vp]),
     "pt_batch_kernel_name": (C.c_char_p, [_vp]),
     "pt_batch_last_kernel": (C.c_char_p, [_vp]),
+    "pt_batch_downscale": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
     "pt_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "pt_host_free": (C.c_int, [_vp]),
     "pt_batch_stream": (_vp, [_vp]),

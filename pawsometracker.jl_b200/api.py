@@ -123,6 +123,76 @@ class _Resampled:
 
 
 # ---------------------------------------------------------------------------
+# diagnostics video (src/diagnose.jl)
+# ---------------------------------------------------------------------------
+DIAGNOSTIC_VIDEO_SIZE = (360, 640)      # src/diagnose.jl:2
+TRACE_BUFFER_SIZE = 100                 # src/diagnose.jl:3
+
+
+class Diagnose:
+    """`Diagnose(file, darker_target)` — src/diagnose.jl:5-24.  Per frame (:30-38): the tracked point scaled to
+    the 360x640 buffer joins a 100-point trail, the frame is `imresize!`d into the buffer (on the device:
+    pt_batch_downscale), label, dot (radius 2) and trail are drawn in white for dark targets / black for light
+    ones, and the buffer goes to the encoder (host, OpenCV — the reference uses VideoIO's writer)."""
+
+    def __init__(self, file: str, darker_target: bool, fps: float = 24.0):
+        import os
+        import cv2
+        self._cv2 = cv2
+        self.label = os.path.splitext(os.path.basename(file))[0]
+        self.buffer = np.zeros(DIAGNOSTIC_VIDEO_SIZE, np.uint8)
+        self.color = 255 if darker_target else 0
+        ext = os.path.splitext(file)[1].lower()
+        fourcc = cv2.VideoWriter_fourcc(*("MJPG" if ext == ".avi" else "mp4v"))
+        self.writer = cv2.VideoWriter(file, fourcc, float(fps), (DIAGNOSTIC_VIDEO_SIZE[1], DIAGNOSTIC_VIDEO_SIZE[0]),
+                                      isColor=False)
+        if not self.writer.isOpened():
+            raise OSError(f"cannot open {file} for writing")
+        self.trace = []                     # CircularBuffer{CartesianIndex{2}}(100)
+        self.ratio = (1.0, 1.0)
+        self.frames_written = 0
+
+    def update_ratio(self, sz):             # update_ratio! (:26-28)
+        self.ratio = (DIAGNOSTIC_VIDEO_SIZE[0] / sz[0], DIAGNOSTIC_VIDEO_SIZE[1] / sz[1])
+
+    def scaled(self, point):
+        return (int(round(point[0] * self.ratio[0])), int(round(point[1] * self.ratio[1])))   # round.(Int, point .* ratio)
+
+    def __call__(self, trckr, point):       # (dia::Diagnose)(img, point) (:30-38)
+        cv2 = self._cv2
+        ij = self.scaled(point)
+        self.trace.append(ij)
+        if len(self.trace) > TRACE_BUFFER_SIZE:
+            self.trace.pop(0)
+        self.buffer[...] = trckr.downscaled(*DIAGNOSTIC_VIDEO_SIZE)                           # imresize!(dia.buffer, img)
+        cv2.putText(self.buffer, self.label, (20, 40), cv2.FONT_HERSHEY_SIMPLEX, 0.7, int(self.color), 1, cv2.LINE_AA)
+        cv2.circle(self.buffer, (ij[1] - 1, ij[0] - 1), 2, int(self.color), -1)               # CirclePointRadius(ij, 2)
+        if len(self.trace) > 1:
+            pts = np.array([[j - 1, i - 1] for i, j in self.trace], np.int32).reshape(-1, 1, 2)
+            cv2.polylines(self.buffer, [pts], False, int(self.color), 1)                      # Path(dia.trace)
+        self.writer.write(self.buffer)
+        self.frames_written += 1
+
+    def close(self):
+        self.writer.release()
+
+
+class _Dont:                                # struct Dont (:42-46)
+    def update_ratio(self, sz):
+        pass
+
+    def __call__(self, trckr, point):
+        pass
+
+    def close(self):
+        pass
+
+
+def diagnose(file, darker_target):
+    return _Dont() if file is None else Diagnose(file, darker_target)
+
+
+# ---------------------------------------------------------------------------
 # start-up helpers
 # ---------------------------------------------------------------------------
 def get_guess(start_location, vid, img):
@@ -158,14 +228,18 @@ def track_one(file, start, stop, target_width, start_location, window_size, dark
     t = stop - start
     n = int(round(fps * t))
     ts = np.linspace(start, stop, n)                            # range(start, stop, n) (:152)
+    dia = dia if dia is not None else _Dont()
     vid = _Resampled(open_video(file), start, t, fps)
     img = vid.read()
+    dia.update_ratio(img.shape)                                 # (:160)
     trckr, ij = get_start_ij_and_tracker(start_location, vid.vid, img, target_width, window_size, darker_target, device)
     indices = [ij]
     try:
+        dia(trckr, ij)
         while not vid.eof() and len(indices) < n:
             vid.read(out=trckr.img)                             # read!(vid, trckr.img.data) (:166)
             indices.append(trckr(indices[-1]))                  # (:167)
+            dia(trckr, indices[-1])                             # (:168)
     finally:
         trckr.close()
     last = len(indices)
@@ -175,12 +249,6 @@ def track_one(file, start, stop, target_width, start_location, window_size, dark
 # ---------------------------------------------------------------------------
 # public API
 # ---------------------------------------------------------------------------
-def _no_diagnostics(diagnostic_file):
-    if diagnostic_file is not None:
-        raise NotImplementedError("diagnostic_file: the diagnostics video (src/diagnose.jl) is outside the "
-                                  "hot-path scope of this build (SURVEY §8f rank 4)")
-
-
 def track(file, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, target_width=25, start_location=None,
           window_size=None, darker_target=True, fps=24, diagnostic_file=None, device=0, parallel=False):
     """`track(file; …)` (src/PawsomeTracker.jl:130-146) or, when `file` is a list,
@@ -191,11 +259,14 @@ def track(file, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, target_width=25, 
                               start_location=start_location, window_size=window_size,
                               darker_target=darker_target, fps=fps, diagnostic_file=diagnostic_file, device=device,
                               parallel=parallel)
-    _no_diagnostics(diagnostic_file)
     if window_size is None:
         window_size = guess_window_size(target_width)
     window_size = fix_window_size(window_size)
-    return track_one(file, start, stop, target_width, start_location, window_size, darker_target, fps, None, device)
+    dia = diagnose(diagnostic_file, darker_target)              # diagnose(...) do dia … end (:143-145)
+    try:
+        return track_one(file, start, stop, target_width, start_location, window_size, darker_target, fps, dia, device)
+    finally:
+        dia.close()
 
 
 def track_segments(files: Sequence, *, start=None, stop=None, target_width=25, start_location=None,
@@ -207,8 +278,9 @@ def track_segments(files: Sequence, *, start=None, stop=None, target_width=25, s
     `start_location` does not depend on the segment before it (`coalesce`, :204), so the file list splits into
     independent CHAINS of segments; the chains advance concurrently as the videos of one TrackerBatch.  The
     result is identical to the serial loop."""
-    _no_diagnostics(diagnostic_file)
     if parallel:
+        if diagnostic_file is not None:
+            raise ValueError("diagnostic_file needs the serial segment loop (one writer, frames in order)")
         return _track_segments_parallel(files, start, stop, target_width, start_location, window_size,
                                         darker_target, fps, device)
     start, stop, start_location = _segment_args(files, start, stop, start_location)
@@ -217,12 +289,16 @@ def track_segments(files: Sequence, *, start=None, stop=None, target_width=25, s
     window_size = fix_window_size(window_size)
     tss, ijs = [], []
     end_location = None
-    for f, t_start, t_stop, loc in zip(files, start, stop, start_location):
-        loc = loc if loc is not None else end_location                            # coalesce (:204)
-        ts_i, ij_i = track_one(f, t_start, t_stop, target_width, loc, window_size, darker_target, fps, None, device)
-        tss.append(ts_i)
-        ijs.append(ij_i)
-        end_location = CartesianIndex(int(ij_i[-1, 0]), int(ij_i[-1, 1]))         # (:206)
+    dia = diagnose(diagnostic_file, darker_target)                                # one writer for all segments (:200)
+    try:
+        for f, t_start, t_stop, loc in zip(files, start, stop, start_location):
+            loc = loc if loc is not None else end_location                        # coalesce (:204)
+            ts_i, ij_i = track_one(f, t_start, t_stop, target_width, loc, window_size, darker_target, fps, dia, device)
+            tss.append(ts_i)
+            ijs.append(ij_i)
+            end_location = CartesianIndex(int(ij_i[-1, 0]), int(ij_i[-1, 1]))     # (:206)
+    finally:
+        dia.close()
     n = sum(len(t) for t in tss)
     step = (tss[0][1] - tss[0][0]) if len(tss[0]) > 1 else 0.0
     ts = tss[0][0] + step * np.arange(n)                                          # range(first, step=…, length=n) (:210)

@@ -1060,6 +1060,24 @@ const char *pt_batch_kernel_name(const pt_batch *b)
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
 }
 
+int pt_batch_downscale(pt_batch *b, int out_h, int out_w, uint8_t *out)
+{
+    if (!b || !out) return fail(PT_ERR_ARG, "NULL argument");
+    if (out_h < 1 || out_w < 1) return fail(PT_ERR_ARG, "output size must be positive");
+    int rc = set_device(b);
+    if (rc) return rc;
+    const void *base; size_t stride, pitch;
+    rc = current_frames(b, &base, &stride, &pitch); if (rc) return rc;
+    const size_t bytes = (size_t)b->n * out_h * out_w;
+    rc = b->d_map.ensure(bytes); if (rc) return rc;
+    cudaError_t e = pt::launch_downscale(base, stride, (int)pitch, b->H, b->W, b->n, b->pixel, out_h, out_w,
+                                         (uint8_t *)b->d_map.p, b->stream);
+    if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(out, b->d_map.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return PT_OK;
+}
+
 int pt_host_alloc(size_t bytes, void **out)
 {
     if (!out || bytes == 0) return fail(PT_ERR_ARG, "bad argument");

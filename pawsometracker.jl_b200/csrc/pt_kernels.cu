@@ -608,4 +608,43 @@ cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Diagnostics downscale — `imresize!(dia.buffer, img)` to 360×640 (src/diagnose.jl:2,33): bilinear
+// interpolation at pixel-centre aligned sample positions, one thread per output pixel, one launch for the
+// current frame of every video.  HBM-bound (reads only the 4 neighbours of each output sample).
+// ---------------------------------------------------------------------------
+template <typename PixT> __device__ __forceinline__ float px_as_u8scale(const PixT *p);
+template <> __device__ __forceinline__ float px_as_u8scale<uint8_t>(const uint8_t *p) { return (float)__ldg(p); }
+template <> __device__ __forceinline__ float px_as_u8scale<float>(const float *p) { return __ldg(p) * 255.0f; }
+
+template <typename PixT>
+__global__ void __launch_bounds__(256)
+downscale_kernel(const void *frames, size_t frame_stride, int pitch, int H, int W, int oh, int ow, uint8_t *out)
+{
+    const int v = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= ow || y >= oh) return;
+    const PixT *frame = reinterpret_cast<const PixT *>(frames) + (size_t)v * frame_stride;
+    const float sy = ((float)y + 0.5f) * ((float)H / (float)oh) - 0.5f;
+    const float sx = ((float)x + 0.5f) * ((float)W / (float)ow) - 0.5f;
+    const float fy = floorf(sy), fx = floorf(sx);
+    const float wy = sy - fy, wx = sx - fx;
+    const int y0 = min(max((int)fy, 0), H - 1), y1 = min(max((int)fy + 1, 0), H - 1);
+    const int x0 = min(max((int)fx, 0), W - 1), x1 = min(max((int)fx + 1, 0), W - 1);
+    const float p00 = px_as_u8scale<PixT>(frame + (size_t)y0 * pitch + x0), p01 = px_as_u8scale<PixT>(frame + (size_t)y0 * pitch + x1);
+    const float p10 = px_as_u8scale<PixT>(frame + (size_t)y1 * pitch + x0), p11 = px_as_u8scale<PixT>(frame + (size_t)y1 * pitch + x1);
+    const float top = p00 + wx * (p01 - p00), bot = p10 + wx * (p11 - p10);
+    const float val = top + wy * (bot - top);
+    out[((size_t)v * oh + y) * ow + x] = (uint8_t)min(max(__float2int_rn(val), 0), 255);
+}
+
+cudaError_t launch_downscale(const void *frames, size_t frame_stride, int pitch, int H, int W, int n, int pixel,
+                             int oh, int ow, uint8_t *out, cudaStream_t s)
+{
+    dim3 grid((unsigned)((ow + 31) / 32), (unsigned)((oh + 7) / 8), (unsigned)n);
+    if (pixel == 0) downscale_kernel<uint8_t><<<grid, 256, 0, s>>>(frames, frame_stride, pitch, H, W, oh, ow, out);
+    else downscale_kernel<float><<<grid, 256, 0, s>>>(frames, frame_stride, pitch, H, W, oh, ow, out);
+    return cudaGetLastError();
+}
+
 } // namespace pt

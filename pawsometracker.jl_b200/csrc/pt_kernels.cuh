@@ -119,4 +119,8 @@ cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int 
                         int pixel, unsigned int *hist, float *fill_out, int *fill_int_out,
                         cudaStream_t s);
 
+// imresize!(dia.buffer, img) (src/diagnose.jl:33): current frame of n videos → [n][oh][ow] u8, bilinear, centre-aligned.
+cudaError_t launch_downscale(const void *frames, size_t frame_stride, int pitch, int H, int W, int n, int pixel,
+                             int oh, int ow, uint8_t *out, cudaStream_t s);
+
 } // namespace pt

@@ -211,6 +211,12 @@ class TrackerBatch:
                                        C.byref(ri), C.byref(rj), C.byref(r)))
         return (oi.value, oj.value), (ri.value, rj.value), r.value
 
+    def downscale(self, out_h: int, out_w: int) -> np.ndarray:
+        """`imresize!` of the current frame of every video to (out_h, out_w) on the device (src/diagnose.jl:33)."""
+        out = np.empty((self.n, int(out_h), int(out_w)), np.uint8)
+        check(lib.pt_batch_downscale(self._h, int(out_h), int(out_w), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
     def rect_argmax_all(self, y0: int, x0: int, wr: int, wc: int, readback: bool = True):
         """The same output rectangle on the current frame of every video, one launch.  Returns
         (ij [n,2], raw_ij [n,2], resp [n]); with readback=False only enqueues the launch."""
@@ -292,6 +298,11 @@ class Tracker:
     def response_map(self, guess) -> np.ndarray:
         self._batch.set_frames([self.img])
         return self._batch.response_map(0, guess)
+
+    def downscaled(self, out_h: int, out_w: int) -> np.ndarray:
+        """`imresize!` of the current host frame (uploaded whole) on the device — diagnostics only."""
+        self._batch.set_frames([self.img])
+        return self._batch.downscale(out_h, out_w)[0]
 
     def close(self):
         self._batch.close()

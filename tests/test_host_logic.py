@@ -79,6 +79,15 @@ def test_segment_length_mismatch_asserts(pkg):
         pkg.track_segments([v, v], start=[0.0], stop=[1.0, 1.0], start_location=[None, None])
 
 
-def test_diagnostics_are_out_of_scope(pkg):
-    with pytest.raises(NotImplementedError):
-        pkg.track(pkg.make_video(), diagnostic_file="x.mp4")
+def test_diagnostics_scaling_and_trail(pkg, tmp_path):
+    """src/diagnose.jl:26-32: ratio = size(buffer) ./ size(img); ij = round.(Int, point .* ratio); 100-point trail."""
+    pytest.importorskip("cv2")
+    d = pkg.Diagnose(str(tmp_path / "d.avi"), True)
+    try:
+        assert d.label == "d" and d.color == 255 and d.buffer.shape == (360, 640)
+        d.update_ratio((1080, 1920))
+        assert d.ratio == (1 / 3, 1 / 3)
+        assert d.scaled((541, 961)) == (180, 320)
+        assert pkg.Diagnose(str(tmp_path / "l.avi"), False).color == 0
+    finally:
+        d.close()

@@ -730,6 +730,51 @@ def test_decode_feeder_pinned_ring_batch(gpu_pkg, tmp_path):
     pa.close()
 
 
+def test_diagnostic_video_and_device_downscale(gpu_pkg, tmp_path):
+    """`diagnostic_file` (src/diagnose.jl): one 360x640 frame per tracked frame with the
+    frame downscaled on the device, dot and trail at the tracked point.  The downscale kernel is checked against
+    the bilinear formula it implements (pixel-centre aligned; the reference's ImageTransformations is not vendored)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(12)
+    H, W = 270, 480
+    f = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    with gpu_pkg.TrackerBatch(2, (H, W), 25, (45, 45), True) as b:
+        b.set_frames([f, 255 - f])
+        got = b.downscale(90, 160)
+    ys = (np.arange(90) + 0.5) * (H / 90) - 0.5
+    xs = (np.arange(160) + 0.5) * (W / 160) - 0.5
+    y0 = np.floor(ys).astype(int); x0 = np.floor(xs).astype(int)
+    wy = (ys - y0)[:, None]; wx = (xs - x0)[None, :]
+    yc0, yc1 = np.clip(y0, 0, H - 1), np.clip(y0 + 1, 0, H - 1)
+    xc0, xc1 = np.clip(x0, 0, W - 1), np.clip(x0 + 1, 0, W - 1)
+    for v, src in enumerate((f, 255 - f)):
+        s_ = src.astype(np.float64)
+        top = s_[yc0][:, xc0] * (1 - wx) + s_[yc0][:, xc1] * wx
+        bot = s_[yc1][:, xc0] * (1 - wx) + s_[yc1][:, xc1] * wx
+        ref = top * (1 - wy) + bot * wy
+        assert np.abs(got[v].astype(np.float64) - ref).max() <= 0.5 + 1e-3
+    # the diagnostics video of a short track
+    nfr = 20
+    tra = gpu_pkg.spiral(0.8 * 135, 600, (135, 240), seed=1)[:nfr]
+    vid = gpu_pkg.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+    out = str(tmp_path / "diag.avi")
+    ts, ij = gpu_pkg.track(vid, stop=nfr / 24.0, target_width=25, start_location=gpu_pkg.CartesianIndex(135, 240),
+                           fps=24, diagnostic_file=out)
+    _, ij_plain = gpu_pkg.track(vid, stop=nfr / 24.0, target_width=25, start_location=gpu_pkg.CartesianIndex(135, 240), fps=24)
+    np.testing.assert_array_equal(ij, ij_plain)                      # diagnostics do not disturb the track
+    cap = cv2.VideoCapture(out)
+    frames = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        frames.append(fr)
+    assert len(frames) == nfr and frames[0].shape[:2] == (360, 640)
+    last = cv2.cvtColor(frames[-1], cv2.COLOR_BGR2GRAY)
+    pi, pj = int(round(ij[-1, 0] * 360 / H)) - 1, int(round(ij[-1, 1] * 640 / W)) - 1
+    assert last[pi, pj] > 200                                        # white dot on the dark disk (MJPG is lossy)
+
+
 def test_plain_c_consumer_of_the_abi(gpu_pkg, oracle, tmp_path):
     """A C program compiled against include/pawsome.h and linked to libpawsome_cuda.so (no Python, no torch):
     the drop-in boundary as a foreign binding sees it."""
