@@ -13,6 +13,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -80,34 +82,84 @@ void make_taps(double tw, bool darker, int pixel, std::vector<float> &rp, std::v
 
 size_t px_size(int pixel) { return pixel == PT_PIX_U8 ? 1 : 4; }
 
+// Process-wide caches of freed buffers.  `track()` builds (and the auto-detect start builds twice) a Tracker per
+// call, the reference's own pattern (src/PawsomeTracker.jl:94,103-105); page-locking and unlocking a staging
+// buffer costs milliseconds each, more than tracking a short clip, so released buffers are parked here (bounded)
+// and handed to the next batch.  Capacities are rounded up to powers of two so they are reusable.
+struct BufPool {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void *> free_;      // (device or -1 for pinned, capacity) → pointer
+    size_t held = 0;
+    static size_t round_cap(size_t bytes)
+    {
+        if (bytes > (64u << 20)) return bytes;                 // large buffers are not pooled: exact size
+        size_t c = 4096;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+    void *get(int key, size_t cap)
+    {
+        std::lock_guard<std::mutex> g(m);
+        auto it = free_.find(std::make_pair(key, cap));
+        if (it == free_.end()) return nullptr;
+        void *p = it->second;
+        free_.erase(it);
+        held -= cap;
+        return p;
+    }
+    bool put(int key, size_t cap, void *p)
+    {
+        std::lock_guard<std::mutex> g(m);
+        if (cap > (64u << 20) || held + cap > (512u << 20)) return false;
+        free_.emplace(std::make_pair(key, cap), p);
+        held += cap;
+        return true;
+    }
+};
+BufPool &pool() { static BufPool *p = new BufPool(); return *p; }     // never destroyed: no CUDA calls at exit
+
 struct PinnedBuf {
     void *p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return PT_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        CU(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
-        cap = bytes;
+        if (p) cudaDeviceSynchronize();                        // regrow: nothing in flight may still use the old buffer
+        release();
+        const size_t c = BufPool::round_cap(bytes);
+        p = pool().get(-1, c);
+        if (!p) CU(cudaHostAlloc(&p, c, cudaHostAllocDefault));
+        cap = c;
         return PT_OK;
     }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    void release()
+    {
+        if (p && !pool().put(-1, cap, p)) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+    }
 };
 
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    int dev = 0;
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return PT_OK;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        CU(cudaMalloc(&p, bytes));
-        cap = bytes;
+        if (p) cudaDeviceSynchronize();                        // regrow: nothing in flight may still use the old buffer
+        release();
+        const size_t c = BufPool::round_cap(bytes);
+        CU(cudaGetDevice(&dev));
+        p = pool().get(dev, c);
+        if (!p) CU(cudaMalloc(&p, c));
+        cap = c;
         return PT_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release()
+    {
+        if (p && !pool().put(dev, cap, p)) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
 };
 
 // Range of the allocation containing p, through the driver entry point (no libcuda link:
@@ -163,6 +215,7 @@ struct pt_batch {
     int L = 0, w = 0, Lpad = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    DevBuf d_arena;                      // backs every small d_* pointer below (one allocation per batch)
     float2 *d_taps_row = nullptr, *d_taps_col = nullptr;
     float *d_fill = nullptr;
     int *d_fill_i = nullptr;
@@ -365,8 +418,16 @@ int upload_frames(pt_batch *b, const void *const *frames, size_t pitch, int slot
                                  (size_t)b->H, cudaMemcpyDefault, s));
         return PT_OK;
     }
-    // pageable source: pack rows into pinned staging (two halves, alternating) then DMA
     const size_t frame_bytes = row_bytes * (size_t)b->H;
+    if (frame_bytes * (size_t)b->n <= (8u << 20) && b->h_stage[0].cap == 0) {
+        // small upload (a single Tracker's frame): page-locking a staging buffer costs milliseconds, more than
+        // letting the driver stage the pageable copy itself
+        for (int v = 0; v < b->n; ++v)
+            CU(cudaMemcpy2DAsync(dbase + dst_stride_b * v, dst_pitch_b, frames[v], src_pitch_b, row_bytes,
+                                 (size_t)b->H, cudaMemcpyHostToDevice, s));
+        return PT_OK;
+    }
+    // pageable source: pack rows into pinned staging (two halves, alternating) then DMA
     const size_t per_half = std::max<size_t>(1, std::min<size_t>((size_t)b->n, (64u << 20) / std::max<size_t>(frame_bytes, 1)));
     for (int h = 0; h < 2; ++h) { rc = b->h_stage[h].ensure(per_half * frame_bytes); if (rc) return rc; }
     int half = 0;
@@ -457,11 +518,11 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     const int L = kernel_len_of(tw);
     const int Lpad = ((L + pt::kTapChunk - 1) / pt::kTapChunk) * pt::kTapChunk;
     CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (pt::generic_smem_bytes(L, Lpad) > (size_t)prop.sharedMemPerBlockOptin)
+    int smem_optin = 0;      // (cudaGetDeviceProperties costs ~20 ms per call; one attribute is microseconds)
+    CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (pt::generic_smem_bytes(L, Lpad) > (size_t)smem_optin)
         return fail(PT_ERR_UNSUPPORTED, "kernel length %d (target_width %g) needs %zu B shared memory, device allows %zu",
-                    L, tw, pt::generic_smem_bytes(L, Lpad), (size_t)prop.sharedMemPerBlockOptin);
+                    L, tw, pt::generic_smem_bytes(L, Lpad), (size_t)smem_optin);
 
     pt_batch *b = new (std::nothrow) pt_batch();
     if (!b) return fail(PT_ERR_NOMEM, "out of host memory");
@@ -490,29 +551,31 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
         cu(cudaEventCreateWithFlags(&b->ev_copy[i], cudaEventDisableTiming), "cudaEventCreate");
         cu(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming), "cudaEventCreate");
     }
-    cu(cudaMalloc(&b->d_taps_row, sizeof(float2) * Lpad), "cudaMalloc taps");
-    cu(cudaMalloc(&b->d_taps_col, sizeof(float2) * Lpad), "cudaMalloc taps");
-    cu(cudaMalloc(&b->d_fill, sizeof(float) * n), "cudaMalloc fill");
-    cu(cudaMalloc(&b->d_fill_i, sizeof(int) * n), "cudaMalloc fill");
-    cu(cudaMalloc(&b->d_guess, sizeof(int2) * n), "cudaMalloc guess");
-    cu(cudaMalloc(&b->d_center, sizeof(int2) * n), "cudaMalloc center");
-    cu(cudaMalloc(&b->d_keys, sizeof(unsigned long long) * n), "cudaMalloc keys");
-    cu(cudaMalloc(&b->d_counters, sizeof(unsigned int) * 3 * n), "cudaMalloc counters");   // [n] completion + [n][2] ticket scratch
-    cu(cudaMalloc(&b->d_hist, sizeof(unsigned int) * pt::kModeScratch * (size_t)n), "cudaMalloc hist");
-    cu(cudaMalloc(&b->d_pos, sizeof(int4) * n), "cudaMalloc pos");
-    cu(cudaMalloc(&b->d_xflag, sizeof(unsigned int) * n), "cudaMalloc xflag");
-    cu(cudaMalloc(&b->d_xpos, sizeof(int2) * n), "cudaMalloc xpos");
-    cu(cudaMalloc(&b->d_resp, sizeof(float) * n), "cudaMalloc resp");
-    if (rc == PT_OK) {
-        cu(cudaMemcpy(b->d_taps_row, trow.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
-        cu(cudaMemcpy(b->d_taps_col, tcol.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
-        cu(cudaMemset(b->d_keys, 0, sizeof(unsigned long long) * n), "memset");
-        cu(cudaMemset(b->d_counters, 0, sizeof(unsigned int) * 3 * n), "memset");
-        cu(cudaMemset(b->d_hist, 0, sizeof(unsigned int) * pt::kModeScratch * (size_t)n), "memset");
-        cu(cudaMemset(b->d_pos, 0, sizeof(int4) * n), "memset");
-        cu(cudaMemset(b->d_xflag, 0, sizeof(unsigned int) * n), "memset");
-        cu(cudaMemset(b->d_xpos, 0, sizeof(int2) * n), "memset");
-        cu(cudaMemset(b->d_resp, 0, sizeof(float) * n), "memset");
+    // one arena for all the small per-batch device buffers: one cudaMalloc, one cudaMemset, one cudaFree
+    {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_trow = take(sizeof(float2) * Lpad), o_tcol = take(sizeof(float2) * Lpad);
+        const size_t o_fill = take(sizeof(float) * n), o_filli = take(sizeof(int) * n);
+        const size_t o_guess = take(sizeof(int2) * n), o_center = take(sizeof(int2) * n);
+        const size_t o_keys = take(sizeof(unsigned long long) * n);
+        const size_t o_cnt = take(sizeof(unsigned int) * 3 * n);                       // [n] completion + [n][2] ticket scratch
+        const size_t o_hist = take(sizeof(unsigned int) * pt::kModeScratch * (size_t)n);
+        const size_t o_pos = take(sizeof(int4) * n), o_resp = take(sizeof(float) * n);
+        const size_t o_xflag = take(sizeof(unsigned int) * n), o_xpos = take(sizeof(int2) * n);
+        if (rc == PT_OK && b->d_arena.ensure(off) != PT_OK) rc = PT_ERR_CUDA;
+        if (rc == PT_OK) {
+            char *a0 = (char *)b->d_arena.p;
+            b->d_taps_row = (float2 *)(a0 + o_trow); b->d_taps_col = (float2 *)(a0 + o_tcol);
+            b->d_fill = (float *)(a0 + o_fill); b->d_fill_i = (int *)(a0 + o_filli);
+            b->d_guess = (int2 *)(a0 + o_guess); b->d_center = (int2 *)(a0 + o_center);
+            b->d_keys = (unsigned long long *)(a0 + o_keys); b->d_counters = (unsigned int *)(a0 + o_cnt);
+            b->d_hist = (unsigned int *)(a0 + o_hist); b->d_pos = (int4 *)(a0 + o_pos); b->d_resp = (float *)(a0 + o_resp);
+            b->d_xflag = (unsigned int *)(a0 + o_xflag); b->d_xpos = (int2 *)(a0 + o_xpos);
+            cu(cudaMemset(b->d_arena.p, 0, off), "memset");
+            cu(cudaMemcpy(b->d_taps_row, trow.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
+            cu(cudaMemcpy(b->d_taps_col, tcol.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
+        }
     }
     if (rc != PT_OK) { pt_batch_destroy(b); return rc; }
     b->h_fill.assign(n, 0);
@@ -531,9 +594,7 @@ void pt_batch_destroy(pt_batch *b)
         if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
         ln.h_crops.release(); ln.h_res.release(); ln.d_crops.release();
     }
-    cudaFree(b->d_taps_row); cudaFree(b->d_taps_col); cudaFree(b->d_fill); cudaFree(b->d_fill_i);
-    cudaFree(b->d_guess); cudaFree(b->d_center); cudaFree(b->d_keys); cudaFree(b->d_counters);
-    cudaFree(b->d_hist); cudaFree(b->d_pos); cudaFree(b->d_resp); cudaFree(b->d_xflag); cudaFree(b->d_xpos);
+    b->d_arena.release();
     for (int i = 0; i < 2; ++i) {
         b->d_frames[i].release(); b->h_stage[i].release();
         if (b->ev_copy[i]) cudaEventDestroy(b->ev_copy[i]);

@@ -50,3 +50,21 @@ config_track("config 1: 480x640, 300 frames, tw=25, start given", 480, 640, 300,
 config_track("config 2: 1080p, 600 of 3000 frames, tw=25, start missing (auto-detect)", 1080, 1920, 600, 25, True, None)
 config_track("config 4: 4K, 60 frames, light target tw=100, window 401", 2160, 3840, 60, 100, False, None, 401)
 config_track("config 4b: 4K, 60 frames, light target tw=100, default window", 2160, 3840, 60, 100, False, None)
+
+# config 5: segmented multi-file video, SAR = 2, non-zero start, fps resampling (serial chain and parallel chains)
+H5, Wd5, sar5, src_fps, fps5 = 1080, 1920, 2, 24.0, 12.0
+_, tra5 = pkg.build_trajectory(0.8 * 540, src_fps, (540, 960), seconds=12.0, seed=0)
+parts = pkg.my_partition(len(tra5), 3)
+segs = [pkg.ArrayVideo(np.stack([pkg.SyntheticVideo(H5, Wd5, tra5[a:b + 1], 25, True, fps=src_fps, sar=sar5).frame(k)
+                                 for k in range(b - a + 1)]), fps=src_fps, sar=sar5) for a, b in parts]
+seg_start = [0.25, 0.0, 0.0]
+seg_stop = [(b - a + 1) / src_fps for a, b in parts]
+x0, y0 = int(tra5[6, 1]), int(tra5[6, 0])
+kw5 = dict(start=seg_start, stop=seg_stop, target_width=25, darker_target=True, fps=fps5)
+dt, (ts5, ij5) = timed("c5", lambda: pkg.track(segs, start_location=[(x0, y0), None, None], **kw5))
+print(f"config 5: 3 segments 1080x960 (SAR 2), start 0.25 s, fps 24->12, chained: {len(ij5)} frames in {dt*1e3:.1f} ms = "
+      f"{len(ij5)/dt:.0f} frames/s")
+locs = [(x0, y0)] + [(int(tra5[a, 1]), int(tra5[a, 0])) for a, _ in parts[1:]]
+dt, (ts5p, ij5p) = timed("c5p", lambda: pkg.track(segs, start_location=locs, parallel=True, **kw5))
+print(f"config 5, every segment with its own start_location, parallel chains: {len(ij5p)} frames in {dt*1e3:.1f} ms = "
+      f"{len(ij5p)/dt:.0f} frames/s")
