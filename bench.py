@@ -573,8 +573,11 @@ def run_gpu(args, ranks):
     cp = (fr + 15) // 16 * 16
     e2e = {"value": world * n * K / dt_fp, "unit": "frames/s",
            "h2d_bytes_per_step": n * fr * cp, "d2h_bytes_per_step": n * 20,
-           "mode": "footprint streaming: per step each video's 109x109 u8 footprint is gathered from its host frame "
-                   "into pinned staging and copied; results are read back every step (pt_batch_track_host mode 0)",
+           "mode": "footprint streaming from pinned host frames (pt_batch_track_host mode 0): the chained kernel reads "
+                   "each video's 109x109 u8 footprint of every step straight from the host frame over PCIe (zero-copy; "
+                   "h2d_bytes = the 109 rows x 112-byte aligned spans it touches) and stores every step's result "
+                   "straight into pinned host memory; the call returns after one stream synchronise; timed by the "
+                   "host clock around the call, frames and results in host memory",
            "ms_per_step": 1e3 * dt_fp / K, "positions_correct": ok_fp}
     kf = min(K, 8)
     dt_fr, ok_fr = e2e_run("frames", 1, kf)
