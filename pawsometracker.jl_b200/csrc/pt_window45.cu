@@ -67,6 +67,11 @@ struct Taps45 {
     float2 cpp[L + 1], cmq[L + 1];
 };
 
+// PRMT selectors of the u8→f32 conversion (byte k of the word under the 2^23 exponent pattern).  Passed as a kernel
+// parameter: as constant-bank operands they cost no instruction, whereas immediates made ptxas keep the 2^23 pattern
+// as the immediate and re-materialise the selectors with MOVs (one per PRMT).
+__constant__ unsigned int c_prmt_sel[4] = {0x7540u, 0x7541u, 0x7542u, 0x7543u};
+
 struct Args45 {
     const void *frames;                 // frame of window 0 at step 0
     size_t frame_stride, step_stride;   // elements
@@ -167,19 +172,19 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
     // one running row pointer (bumped by NWARPS rows per load): two integer instructions per load instead of a
     // fresh 64-bit row-times-pitch product
     const uint8_t *rowp = frame + ((long long)(fy0 + warp) * pitch + X);   // only dereferenced when valid
-    const long long rstep = (long long)NWARPS * pitch;
+    const unsigned long long rstep = (unsigned long long)(NWARPS * pitch);
+    unsigned long long addr = reinterpret_cast<unsigned long long>(rowp);
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
         const int Y = fy0 + f;
         const bool ok = wordok && (f < NROWS) && (kInterior || ((Y >= 0) && (Y < H)));
         wd[r] = fillw;
-        if (ok) wd[r] = __ldg(reinterpret_cast<const unsigned int *>(rowp));
-        rowp += rstep;
+        if (ok) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(wd[r]) : "l"(addr));
+        addr += rstep;                                       // one 64-bit add per load
     }
     const float cst = 8388608.0f + fill;
-    unsigned int magic;                                     // 2^23 exponent pattern kept in a register so that the
-    asm("mov.b32 %0, 0x4B000000;" : "=r"(magic));           // PRMT selectors are immediates (no selector MOVs)
+    const unsigned int magic = 0x4B000000u;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
@@ -189,7 +194,7 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
             float *dst = s_in + f * PIN;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float val = __uint_as_float(__byte_perm(w, magic, 0x7540 + k)) - cst;
+                const float val = __uint_as_float(__byte_perm(w, magic, c_prmt_sel[k])) - cst;
                 if (cok[k]) dst[col[k]] = val;
             }
         }
@@ -469,6 +474,16 @@ __device__ __forceinline__ int rot_window(int slot, int t, int R, int m, int nh)
     if (u >= m) u -= m;
     return u;
 }
+// the same with the two remainders (nh·t) mod R and (nh·t) mod m carried along by the caller (no division per step)
+__device__ __forceinline__ int rot_window_rem(int slot, int remR, int remM, int R, int m)
+{
+    int k = slot - remR;
+    if (k < 0) k += R;
+    if (k >= m) return -1;
+    int u = remM + k;
+    if (u >= m) u -= m;
+    return u;
+}
 
 template <typename PixT>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
@@ -493,9 +508,16 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
     int prev_v = -1;
     int2 g = make_int2(0, 0);
     float fill = 0.f;
+    // (nh·t) mod R and (nh·t) mod m for the current step and the next one, advanced by additions (nh < m < R)
+    int remR = 0, remM = 0, remR1 = nh, remM1 = nh;
+    int v_next = rot_window_rem(slot, 0, 0, R, m);
     for (int t = 0; t < a.T; ++t) {
         const unsigned int it = (unsigned int)t;
-        const int v = rot_window(slot, t, R, m, nh);
+        const int v = v_next;
+        v_next = rot_window_rem(slot, remR1, remM1, R, m);          // holder of this slot at step t + 1
+        remR = remR1; remM = remM1;
+        remR1 += nh; if (remR1 >= R) remR1 -= R;
+        remM1 += nh; if (remM1 >= m) remM1 -= m;
         if (v < 0) { prev_v = -1; continue; }
         if (v != prev_v) {
             fill = a.fill[v];
@@ -589,7 +611,7 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
                 if (t == a.T - 1) {
                     a.out_pos[v] = p; a.out_resp[v] = resp;
                     if (a.next_guess) a.next_guess[v] = make_int2(ci, cj);
-                } else if (rot_window(slot, t + 1, R, m, nh) != v) {
+                } else if (v_next != v) {
                     // the window hops to another SM for the next step: publish the guess, then the flag (release)
                     a.xpos[v] = make_int2(ci, cj);
                     const unsigned int f = (unsigned int)(t + 1);
