@@ -457,14 +457,14 @@ def run_gpu(args, ranks):
     ach_tflops = flops_launch / launch_s / 1e12
     ach_gbs = bytes_launch / launch_s / 1e9
     t_roof = max(flops_launch / (fp32_peak * 1e12), bytes_launch / (hbm_peak * 1e9))
-    # DRAM traffic of this kernel from profiles/r01_window45_final_ncu_full_selected.csv (one `ncu --set full`
-    # capture of a 20-step launch: dram read 209.1 MB + write 5.0 MB): 10.70 MB per 256-video step
-    traffic_per_step = 10.70e6 if batch_kernel in ("dog_window45_argmax", "dog_window45_rot") else None
+    # DRAM traffic of this kernel from profiles/r01_window45_rot_ncu_full_selected.csv (one `ncu --set full`
+    # capture of a 20-step launch: dram read 209.1 MB + write 4.4 MB): 10.67 MB per 256-video step
+    traffic_per_step = 10.67e6 if batch_kernel in ("dog_window45_argmax", "dog_window45_rot") else None
     roofline = {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach_tflops / fp32_peak,
                 "traffic": traffic_per_step * steps_per_launch if traffic_per_step else None,
                 "traffic_note": "dram__bytes_read+write per launch scaled from the ncu --set full capture in profiles/ "
-                                "(10.70 MB per 256-video step vs 3.05 MB algorithmic: 109-byte rows inside 128-byte "
+                                "(10.67 MB per 256-video step vs 3.05 MB algorithmic: 109-byte rows inside 128-byte "
                                 "lines, plus the deliberate L2 prefetch of the 153-row region the next step can touch; "
                                 "DRAM is at 4 % of its peak)",
                 "kernel": batch_kernel,
