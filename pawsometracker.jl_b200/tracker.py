@@ -258,6 +258,7 @@ class Tracker:
     def __init__(self, img: np.ndarray, target_width, window_size, darker_target, device: int = 0):
         if img.ndim != 2:
             raise ValueError("img must be a 2-D grayscale frame")
+        self._call = None
         self.img = np.ascontiguousarray(img)
         self.sz = tuple(int(s) for s in self.img.shape)
         ws = (int(window_size[0]), int(window_size[1]))
@@ -269,6 +270,16 @@ class Tracker:
         self._batch.set_frames([self.img])
         self.fillvalue = int(self._batch.compute_fill()[0])
         self.last_response = float("nan")
+
+    @property
+    def img(self) -> np.ndarray:
+        """The writable host frame (`trckr.img.data`, :166).  Fill it in place (`read(out=trckr.img)`); assigning a new
+        array is allowed too and re-targets the per-call argument buffers."""
+        return self._img
+
+    @img.setter
+    def img(self, arr):
+        self._img = arr
         self._call = None
 
     def __call__(self, guess):
