@@ -247,7 +247,7 @@ struct pt_batch {
     const void *bound_base = nullptr;
     size_t bound_stride = 0, bound_pitch = 0;
     // trajectory buffer for chained steps
-    DevBuf d_traj_pos, d_traj_resp, d_map, d_ptrs, d_xkeys, d_xcnt;
+    DevBuf d_traj_pos, d_traj_resp, d_map, d_ptrs;
     PinnedBuf h_traj, h_ptrs;
     PinnedBuf h_stage[2], h_out;
     std::vector<pt_lane> lanes;
@@ -289,7 +289,6 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     a.T = 1; a.step_stride = 0;
     a.h_taps = b->h_taps.data();
     a.frame_ptrs = nullptr;
-    a.xkeys = nullptr; a.xcnt = nullptr;
     a.xflag = (nwin == b->n) ? b->d_xflag : nullptr;     // whole-batch launches only (one stream at a time)
     a.xpos = b->d_xpos;
     (void)nwin;
@@ -330,31 +329,11 @@ cudaError_t launch_windows(const pt_batch *b, pt::WinArgs &a, int nwin, cudaStre
 
 int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
 {
-    cudaError_t e;
-    bool done = false;
-    static const bool quad_enabled = getenv("PT_ENABLE_QUAD") != nullptr;
-    if (quad_enabled && b->use45 && !a.rect_mode && !a.map_out) {
-        // experimental: 4 CTAs per window (needs all 4n CTAs co-resident and u8 frames)
-        const size_t slots = (size_t)nwin * (size_t)(a.T > 0 ? a.T : 1);
-        int rc = b->d_xkeys.ensure(slots * sizeof(unsigned long long)); if (rc) return rc;
-        rc = b->d_xcnt.ensure(slots * sizeof(unsigned int)); if (rc) return rc;
-        a.xkeys = (unsigned long long *)b->d_xkeys.p; a.xcnt = (unsigned int *)b->d_xcnt.p;
-        if (pt::window45_quad_supported(a, nwin, b->pixel)) {
-            CU(cudaMemsetAsync(a.xkeys, 0, slots * sizeof(unsigned long long), s));
-            CU(cudaMemsetAsync(a.xcnt, 0, slots * sizeof(unsigned int), s));
-            e = pt::launch_window45_quad(a, nwin, s);
-            done = true;
-        }
-    }
-    if (!done) {
-        e = launch_windows(b, a, nwin, s);
-        if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
-            b->last_kernel = pt::window45_uses_rot(a, nwin) ? pt::window45_rot_name() : pt::window45_name();
-        else if (b->use45 && pt::rect45_supported(a, b->pixel)) b->last_kernel = pt::rect45_name();
-        else b->last_kernel = b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
-    } else {
-        b->last_kernel = pt::window45_quad_name();
-    }
+    const cudaError_t e = launch_windows(b, a, nwin, s);
+    if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
+        b->last_kernel = pt::window45_uses_rot(a, nwin) ? pt::window45_rot_name() : pt::window45_name();
+    else if (b->use45 && pt::rect45_supported(a, b->pixel)) b->last_kernel = pt::rect45_name();
+    else b->last_kernel = b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     b->launches += 1;
     return PT_OK;
@@ -601,7 +580,7 @@ void pt_batch_destroy(pt_batch *b)
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
     }
     b->d_traj_pos.release(); b->d_traj_resp.release(); b->d_map.release(); b->h_out.release();
-    b->d_ptrs.release(); b->h_traj.release(); b->h_ptrs.release(); b->d_xkeys.release(); b->d_xcnt.release();
+    b->d_ptrs.release(); b->h_traj.release(); b->h_ptrs.release();
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     delete b;
@@ -1113,9 +1092,6 @@ const char *pt_batch_kernel_name(const pt_batch *b)
     pt::WinArgs a;
     memset(&a, 0, sizeof a);
     a.wr = b->wr; a.wc = b->wc; a.L = b->L; a.w = b->w; a.h_taps = b->h_taps.data();
-    if (b->use45 && b->pixel == PT_PIX_U8 && getenv("PT_ENABLE_QUAD") && a.L == 65 && a.wr == 45 && a.wc == 45 &&
-        b->n <= pt::window45_quad_max_windows())
-        return pt::window45_quad_name();
     if (b->use45 && pt::window45_supported(a, b->pixel)) return pt::window45_name();
     if (b->use45 && a.L == 65 && !getenv("PT_DISABLE_RECT45") && (long long)a.wr * a.wc >= 24 * 24) return pt::rect45_name();
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";

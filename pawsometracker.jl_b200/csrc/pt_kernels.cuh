@@ -43,8 +43,6 @@ struct WinArgs {
     size_t step_stride;
     const void *const *frame_ptrs;  // optional DEVICE array [T][n] of frame base pointers (overrides frames/strides):
                                // used for zero-copy reads of pinned host frames (specialised kernel only)
-    unsigned long long *xkeys; // [n][T] cross-CTA argmax keys   } exchange scratch of the 4-CTA-per-window kernel,
-    unsigned int *xcnt;        // [n][T] arrival counters        } zeroed by the launcher's caller before each launch
     unsigned int *xflag;       // [n] hand-off flags   } dog_window45_rot (windows hopping between SMs); zero between launches,
     int2 *xpos;                // [n] hand-off guesses } the kernel leaves them zeroed
     const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
@@ -105,12 +103,6 @@ long long *window45_debug_ptr();   // phase-timestamp buffer [n][T][6] (profilin
 bool rect45_supported(const WinArgs &a, int pixel);
 cudaError_t launch_rect45(const WinArgs &a, int n, int pixel, cudaStream_t s);
 const char *rect45_name();
-
-// Second-generation specialised kernel: 4 CTAs per window, u8 frames, cooperative launch.
-bool window45_quad_supported(const WinArgs &a, int n, int pixel);
-int window45_quad_max_windows();
-cudaError_t launch_window45_quad(const WinArgs &a, int n, cudaStream_t s);
-const char *window45_quad_name();
 
 // fillvalue = mode(frame) (src/PawsomeTracker.jl:47) for n frames.
 // hist: [n][kModeScratch] unsigned scratch, zero before the first call and left zeroed by every call.

@@ -91,7 +91,7 @@ def test_generic_kernel_on_default_geometry(gpu_pkg, oracle, monkeypatch):
     generic streaming kernel on the same frames so both stay parity-checked."""
     f = disk_frame(480, 640, 200, 300, 12)
     b = gpu_pkg.TrackerBatch(1, f.shape, 25, (45, 45), True)
-    assert b.kernel_name in ("dog_window45_argmax", "dog_window45_quad")
+    assert b.kernel_name == "dog_window45_argmax"
     b.close()
     monkeypatch.setenv("PT_DISABLE_WINDOW45", "1")
     b = gpu_pkg.TrackerBatch(1, f.shape, 25, (45, 45), True)

@@ -15,13 +15,12 @@ dev = torch.device("cuda", 0)
 pos = bench.orbit_positions(n, 0)
 ring = bench.render_ring_device(torch, pos, 16 * ((T + 15) // 16), dev)
 b = pkg.TrackerBatch(n, (H, W), bench.TW, (bench.WS, bench.WS), True)
-quad = b.kernel_name.endswith("quad")
-NC = 4 * n if quad else n
+NC = n
 print("kernel:", b.kernel_name)
 b.bind_device_frames(ring.data_ptr(), H * W, W)
 b.set_fill(128)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-names = ["stage", "row", "col", "exchange"] if quad else ["stage", "row", "col", "reduce"]
+names = ["stage", "row", "col", "reduce"]
 for label in ("cold (L2 flushed)", "warm (same slots again)", "cold again"):
     if label.startswith("cold"):
         flush.fill_(1)
@@ -41,9 +40,6 @@ for label in ("cold (L2 flushed)", "warm (same slots again)", "cold again"):
     ms = e0.elapsed_time(e1)
     d = dbg.cpu().numpy()
     assert np.array_equal(ij, bench.truth_for_steps(pos, T))
-    if quad:
-        print(f"== {label}: kernel {ms*1e3:.1f} us = {ms*1e3/T:.2f} us/step (4-CTA kernel: no per-window timing view)")
-        continue
     smid = d[:, :, 0] & 0xFF
     gt = d[:, :, 0] >> 8
     ph = np.diff(d[:, :, 1:], axis=2)                       # (n, T, 4): stage, row, col, reduce+publish
