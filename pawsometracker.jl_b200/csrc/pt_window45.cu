@@ -828,14 +828,17 @@ static int sm_count()
     return sms;
 }
 
-// S < n < 2S with few empty slots (at most n/4: every step nh windows hop), frames in HBM, more than one
-// step: rotate the empty slots (dog_window45_rot)
+// S < n < 2S with not too many empty slots, frames in HBM, more than one step: rotate the empty slots
+// (dog_window45_rot)
 bool window45_uses_rot(const WinArgs &a, int n)
 {
     const char *rot_env = getenv("PT_W45_ROT");
     const int rot_on = rot_env ? atoi(rot_env) : 1;
     const int sms = sm_count();
-    return rot_on && a.xflag && a.xpos && !a.frame_ptrs && a.T > 1 && n > sms && n < 2 * sms && 4 * (2 * sms - n) <= n;
+    // every step nh = 2S − n windows hop (≈ 2.5 K cycles of hand-off latency each): measured worthwhile up to
+    // nh ≈ 0.7·n (n ≥ 1.18·S: 9.3 vs 9.9 µs per step at n = 180, break-even at n = 160); PT_W45_ROT=2 forces it
+    const bool few_holes = rot_on == 2 || 10 * (2 * sms - n) <= 7 * n;
+    return rot_on && a.xflag && a.xpos && !a.frame_ptrs && a.T > 1 && n > sms && n < 2 * sms && few_holes;
 }
 
 const char *window45_rot_name() { return "dog_window45_rot"; }

@@ -563,11 +563,11 @@ def test_large_batch_1080p_properties(gpu_pkg):
     assert np.all(resp > 0.08)
 
 
-@pytest.mark.parametrize("n,T", [(1, 1), (3, 5), (149, 4), (300, 3), (700, 2), (256, 9), (240, 7), (295, 5)])
+@pytest.mark.parametrize("n,T", [(1, 1), (3, 5), (149, 4), (300, 3), (700, 2), (256, 9), (240, 7), (295, 5), (180, 6)])
 def test_batch_sizes_exercise_cta_video_loop(gpu_pkg, oracle, n, T):
     """dog_window45_argmax hosts two videos per CTA and loops `v += 2·#CTAs`: cover one video, an odd
     count just above the SM count (lone second halves), and more videos than one wave holds; with
-    1.6·#SMs <= n < 2·#SMs and T > 1 the chained call runs dog_window45_rot (windows hop between SMs while
+    1.18·#SMs <= n < 2·#SMs and T > 1 the chained call runs dog_window45_rot (windows hop between SMs while
     the empty slots rotate), which must agree with the per-step launches step by step.  Every
     video has its own frame content; spot-check a sample of videos against the oracle loop, all of them
     against ground truth, and the per-step path against the chained one."""

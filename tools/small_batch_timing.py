@@ -8,7 +8,7 @@ import torch, bench, pt_import
 pkg = pt_import.load()
 H, W, T = bench.H, bench.W, 32
 dev = torch.device("cuda", 0)
-for n in (1, 32, 100, 148):
+for n in [int(x) for x in sys.argv[1:]] or (1, 32, 100, 148):
     pos = bench.orbit_positions(n, 0)
     ring = bench.render_ring_device(torch, pos, T, dev)
     b = pkg.TrackerBatch(n, (H, W), bench.TW, (bench.WS, bench.WS), True)
