@@ -65,6 +65,9 @@ typedef struct pt_tracker pt_tracker; /* one Tracker == a pt_batch of 1 */
 PT_API int pt_version(void);
 PT_API const char *pt_last_error(void); /* thread-local, never NULL */
 PT_API int pt_device_count(void);       /* number of CUDA devices, or a negative pt_status */
+/* Videos per batch that fill `device` evenly: two windows per SM (296 on a B200).  Multiples of it keep every SM
+ * busy with two windows; batches between 1.18x and 2x the SM count are balanced by dog_window45_rot. */
+PT_API int pt_preferred_batch(int device);
 
 /* ---- scalar helpers (host arithmetic, no device needed) ------------------- */
 /* get_sigma — src/PawsomeTracker.jl:30 */

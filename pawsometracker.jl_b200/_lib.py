@@ -42,6 +42,7 @@ SIGNATURES = {
     "pt_version": (C.c_int, []),
     "pt_last_error": (C.c_char_p, []),
     "pt_device_count": (C.c_int, []),
+    "pt_preferred_batch": (C.c_int, [C.c_int]),
     "pt_sigma": (C.c_double, [C.c_double]),
     "pt_kernel_len": (C.c_int, [C.c_double]),
     "pt_default_window": (C.c_int, [C.c_double]),

@@ -464,6 +464,15 @@ int pt_device_count(void)
 }
 
 double pt_sigma(double tw) { return sigma_of(tw); }
+int pt_preferred_batch(int device)
+{
+    int ndev = 0, sms = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PT_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    return 2 * sms;
+}
+
 int pt_kernel_len(double tw) { return tw > 0 ? kernel_len_of(tw) : fail(PT_ERR_ARG, "target_width must be > 0"); }
 int pt_default_window(double tw) { return 4 * (int)std::ceil(sigma_of(tw)) + 1; }
 
