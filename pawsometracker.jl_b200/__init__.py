@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     Diagnose,
     get_guess,
     get_start_ij_and_tracker,
+    split_chains,
     track,
     track_batch,
     track_one,

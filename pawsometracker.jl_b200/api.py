@@ -361,18 +361,24 @@ class _Chain:
         self.count += 1
 
 
-def _track_segments_parallel(files, start, stop, target_width, start_location, window_size, darker_target, fps, device):
-    start, stop, start_location = _segment_args(files, start, stop, start_location)
-    if window_size is None:
-        window_size = guess_window_size(target_width)
-    window_size = fix_window_size(window_size)
-    # split into chains: a segment with its own start_location starts a new chain
+def split_chains(files, start, stop, start_location):
+    """Independent chains of a segmented video: a segment with its own start_location starts a new chain, a
+    `missing` one continues from the end of its predecessor (`coalesce(loc, end_location)`, :204).
+    Returns [[(file index, file, t_start, t_stop, loc), …], …]."""
     groups = []
     for i, (f, t0, t1, loc) in enumerate(zip(files, start, stop, start_location)):
         if i == 0 or loc is not None:
             groups.append([])
         groups[-1].append((i, f, t0, t1, loc))
-    chains = [_Chain(g, fps) for g in groups]
+    return groups
+
+
+def _track_segments_parallel(files, start, stop, target_width, start_location, window_size, darker_target, fps, device):
+    start, stop, start_location = _segment_args(files, start, stop, start_location)
+    if window_size is None:
+        window_size = guess_window_size(target_width)
+    window_size = fix_window_size(window_size)
+    chains = [_Chain(g, fps) for g in split_chains(files, start, stop, start_location)]
     nc = len(chains)
     cur = [c.next_frame() for c in chains]
     if any(x is None for x in cur):

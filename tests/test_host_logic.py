@@ -91,3 +91,14 @@ def test_diagnostics_scaling_and_trail(pkg, tmp_path):
         assert pkg.Diagnose(str(tmp_path / "l.avi"), False).color == 0
     finally:
         d.close()
+
+
+def test_segment_chains_split_at_explicit_start_locations(pkg):
+    """`coalesce(loc, end_location)` (:204) links a segment to its predecessor only when its own
+    start_location is missing."""
+    files = list("abcdef")
+    locs = [None, None, pkg.CartesianIndex(5, 6), None, (7, 8), pkg.CartesianIndex(1, 1)]
+    chains = pkg.split_chains(files, [0.0] * 6, [1.0] * 6, locs)
+    assert [[seg[0] for seg in c] for c in chains] == [[0, 1], [2, 3], [4], [5]]
+    assert chains[0][0][4] is None and chains[1][0][4] == pkg.CartesianIndex(5, 6) and chains[1][1][4] is None
+    assert [len(c) for c in pkg.split_chains(files, [0.0] * 6, [1.0] * 6, [None] * 6)] == [6]
