@@ -49,6 +49,11 @@ class ArrayVideo:
         np.copyto(out, f)
         return out
 
+    def frame_ref(self, k: int):
+        """The stored frame itself (no copy) when it can be handed to the tracker as it is, else None."""
+        f = self.frames[k]
+        return f if isinstance(f, np.ndarray) and f.ndim == 2 and f.strides[1] == f.itemsize else None
+
 
 class CvVideo:
     """A real video file decoded on the host with OpenCV's FFmpeg backend to
@@ -83,6 +88,10 @@ class CvVideo:
             return g
         np.copyto(out, g)
         return out
+
+    def frame_ref(self, k: int):
+        """The freshly decoded GRAY8 frame: it is a new array anyway, the tracker can read it in place."""
+        return self.frame(k)
 
 
 def open_video(file):
@@ -119,6 +128,19 @@ class _Resampled:
             raise EOFError
         f = self.vid.frame(self._src_index(self.k), out)
         self.k += 1
+        return f
+
+    def read_ref(self):
+        """Next frame by reference when the source can give one (no copy into the tracker's buffer), else None
+        (the caller then falls back to `read(out=…)`, the `read!` of :166)."""
+        get = getattr(self.vid, "frame_ref", None)
+        if get is None:
+            return None
+        if self.eof():
+            raise EOFError
+        f = get(self._src_index(self.k))
+        if f is not None:
+            self.k += 1
         return f
 
 
@@ -236,8 +258,17 @@ def track_one(file, start, stop, target_width, start_location, window_size, dark
     indices = [ij]
     try:
         dia(trckr, ij)
+        own = trckr.img                                         # the tracker's private buffer (trckr.img.data)
         while not vid.eof() and len(indices) < n:
-            vid.read(out=trckr.img)                             # read!(vid, trckr.img.data) (:166)
+            f = vid.read_ref()                                  # a frame the source already holds in host memory:
+            if f is not None and f.shape == trckr.sz and f.dtype == own.dtype:
+                trckr.img = f                                   # … is tracked in place (no 2 MB copy per frame),
+            else:
+                if f is not None:
+                    np.copyto(own, f)
+                else:
+                    vid.read(out=own)                           # else read!(vid, trckr.img.data) (:166)
+                trckr.img = own
             indices.append(trckr(indices[-1]))                  # (:167)
             dia(trckr, indices[-1])                             # (:168)
     finally:

@@ -280,7 +280,10 @@ class Tracker:
     @img.setter
     def img(self, arr):
         self._img = arr
-        self._call = None
+        c = self._call
+        if c is not None:                   # re-target the cached argument buffers (the ctypes arrays are kept)
+            c[1][0] = arr.ctypes.data
+            c[2] = _check_frame(arr, self.sz[0], self.sz[1], self._batch.pixel)
 
     def __call__(self, guess):
         # a tracker is a batch of one: footprint streaming of the current host frame.  This is the per-frame
@@ -288,8 +291,8 @@ class Tracker:
         c = self._call
         if c is None:
             pitch = _check_frame(self.img, self.sz[0], self.sz[1], self._batch.pixel)
-            c = self._call = ((C.c_int32 * 2)(), (C.c_void_p * 1)(self.img.ctypes.data), pitch,
-                              (C.c_int32 * 2)(), (C.c_float * 1)())
+            c = self._call = [(C.c_int32 * 2)(), (C.c_void_p * 1)(self.img.ctypes.data), pitch,
+                              (C.c_int32 * 2)(), (C.c_float * 1)()]
         g, ptrs, pitch, out, resp = c
         g[0], g[1] = int(guess[0]), int(guess[1])
         h = self._batch._h
