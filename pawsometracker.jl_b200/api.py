@@ -381,7 +381,8 @@ class _Chain:
         while not self.done:
             first = self.count == 0
             if (first or self.count < self.n) and not self.vid.eof():      # read(vid) :159, loop condition :162
-                return self.vid.read(), first
+                f = self.vid.read_ref()                                    # by reference when the source allows
+                return (f if f is not None else self.vid.read()), first
             self._open_next()
         return None
 
