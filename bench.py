@@ -299,7 +299,7 @@ def run_gpu(args, ranks):
     seed = 1000 * ranks.rank
 
     # ---- resident workload: ring of step-slots in HBM, never re-read inside a timed region
-    slots = PERIOD * int(np.ceil(min(K + Wm, 64) / PERIOD))
+    slots = PERIOD * int(np.ceil(min(K + Wm, 112) / PERIOD))   # ≤ 112 step-slots = 59 GB of HBM
     pos = orbit_positions(n, seed)
     ring = render_ring_device(torch, pos, slots, device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
