@@ -287,6 +287,7 @@ def run_gpu(args, ranks):
     import torch
 
     import pt_import
+    from tools import benchlib
     pkg = pt_import.load()
     ndev = pkg.lib.pt_device_count()
     if ndev < 1:
@@ -341,7 +342,7 @@ def run_gpu(args, ranks):
     if True:
         rep = 0
         while True:
-            pkg.lib.pt_flush_l2(flush.data_ptr(), flush.numel(), batch.stream)      # untimed: cold L2 for every repeat
+            benchlib.flush_l2(flush.data_ptr(), flush.numel(), batch.stream)      # untimed: cold L2 for every repeat
             batch.set_guess(pos[0])
             run_chain(0, Wm)                                                         # warm-up steps (untimed)
             ranks.barrier()
@@ -368,7 +369,7 @@ def run_gpu(args, ranks):
     value = world * n * K / (ms_K * 1e-3)
 
     # ---- mode(frame) = fill value of each video's first frame (src/PawsomeTracker.jl:47): one HBM pass
-    pkg.lib.pt_flush_l2(flush.data_ptr(), flush.numel(), batch.stream)
+    benchlib.flush_l2(flush.data_ptr(), flush.numel(), batch.stream)
     md = []
     for k in range(3):
         batch.bind_device_frames(ring.data_ptr() + ((k + 1) % slots) * step_stride, H * W, W)   # a slot not in L2
@@ -415,7 +416,7 @@ def run_gpu(args, ranks):
         ok2 = bool(np.array_equal(chk2, truth_for_steps(pos2, min(Wm + K, slots2))))
         ms2 = []
         for _ in range(10):
-            pkg.lib.pt_flush_l2(flush.data_ptr(), flush.numel(), b2.stream)
+            benchlib.flush_l2(flush.data_ptr(), flush.numel(), b2.stream)
             b2.set_guess(pos2[0])
             chain2(0, Wm)
             torch.cuda.synchronize(device)
@@ -441,10 +442,11 @@ def run_gpu(args, ranks):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    tf = C.c_double()
-    tf2 = C.c_double()
-    pkg._lib.check(pkg.lib.pt_measure_fp32_peak(dev_index, 0, 5, C.byref(tf)))
-    pkg._lib.check(pkg.lib.pt_measure_fp32_peak(dev_index, 1, 5, C.byref(tf2)))
+    class _V:                                    # (keeps the .value spelling used below)
+        def __init__(self, v):
+            self.value = v
+    tf = _V(benchlib.fp32_peak(dev_index, 0, 5))
+    tf2 = _V(benchlib.fp32_peak(dev_index, 1, 5))
     fp32_peak = max(tf.value, tf2.value)
     if balanced:
         balanced["frac_fp32"] = balanced["achieved_tflops"] / fp32_peak
@@ -468,7 +470,7 @@ def run_gpu(args, ranks):
                                 "lines, plus the deliberate L2 prefetch of the 153-row region the next step can touch; "
                                 "DRAM is at 4 % of its peak)",
                 "kernel": batch_kernel,
-                "peak_source": "measured in this run (pt_measure_fp32_peak: dependent FFMA chains, best of 5; "
+                "peak_source": "measured in this run (ptb_measure_fp32_peak of libpawsome_bench.so: dependent FFMA chains, best of 5; "
                                f"scalar {tf.value:.1f}, f32x2 {tf2.value:.1f} TFLOP/s); nominal {NOMINAL_FP32_TFLOPS:.1f}",
                 "launches_in_timed_region": int(timed_launches), "steps_per_launch": steps_per_launch,
                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch,
@@ -509,7 +511,7 @@ def run_gpu(args, ranks):
     fullframe_ok = fullframe_ok and bool(np.array_equal(ijm, pos[0, :NFF]))
     ffb_ms = []
     for _ in range(5):
-        pkg.lib.pt_flush_l2(flush.data_ptr(), flush.numel(), many.stream)
+        benchlib.flush_l2(flush.data_ptr(), flush.numel(), many.stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(device)
         with torch.cuda.stream(extm):

@@ -24,7 +24,10 @@
  *   - there is NO CPU fallback: every compute entry point runs CUDA kernels
  *     and fails with PT_ERR_CUDA when no device is usable.
  *   - a handle is not thread-safe; distinct handles may be used from distinct
- *     host threads concurrently (reference: one Tracker per track() call).
+ *     host threads concurrently, on the same or on different devices (reference:
+ *     one Tracker per track() call).  The library keeps no mutable process-wide
+ *     state except a mutex-guarded pool of released buffers and a one-time,
+ *     mutex-guarded per-device initialisation.
  */
 #ifndef PAWSOME_H
 #define PAWSOME_H
@@ -164,10 +167,19 @@ PT_API int pt_batch_response_map(pt_batch *b, int v, int gi, int gj, float *out_
 /* Asynchronous variants used by the measurement harness: launch T chained
  * steps on `stream` (a cudaStream_t, NULL = the batch's own stream) without
  * synchronising; results stay in the device trajectory buffer until
- * pt_batch_read_track. */
+ * pt_batch_read_track.  A batch runs on ONE stream at a time: passing a different
+ * stream first waits for the batch's earlier work, and destroy / pt_batch_read_track /
+ * the next call on the batch wait for the caller's stream. */
 PT_API int pt_batch_track_device_async(pt_batch *b, const void *dev_base, size_t step_stride,
                                 size_t frame_stride, size_t pitch, int T, void *stream);
 PT_API int pt_batch_read_track(pt_batch *b, int T, int32_t *out_ij, float *out_resp);
+
+/* Per-handle tuning / debugging knobs (parity tests pin kernel variants with them).  The process-wide defaults
+ * come from PT_* environment variables read once at the first pt_batch_create.  Names: "window45" (0: force the
+ * generic kernel), "rect45", "rot" (0 off / 1 auto / 2 always), "skew", "r45_chunks" (0 = cost model),
+ * "generic_target", "mode_slow", "zero_copy", "host_lanes", "cluster" (0 auto / 1 off / 2, 4, 8 CTAs per lone
+ * window), "bulk" (TMA staging of the cluster kernel).  Unknown name or value out of range: PT_ERR_ARG. */
+PT_API int pt_batch_set_option(pt_batch *b, const char *name, int value);
 
 /* Introspection for the harness: kernels launched by this handle so far, and
  * the name of the window kernel variant the current geometry dispatches to. */
@@ -223,18 +235,6 @@ PT_API int pt_batch_downscale(pt_batch *b, int out_h, int out_w, uint8_t *out);
  * staging copy: pt_batch_track_host recognises such frames and runs the whole frame loop as one launch. */
 PT_API int pt_host_alloc(size_t bytes, void **out);
 PT_API int pt_host_free(void *p);
-
-/* ---- measurement helpers (bench.py) ---------------------------------------- */
-/* FP32 FMA throughput of `device` in TFLOP/s (2 flops per FMA): packed=0 plain
- * FFMA, packed=1 fma.rn.f32x2.  The measured denominator of the FP32 roofline. */
-PT_API int pt_measure_fp32_peak(int device, int packed, int reps, double *tflops);
-/* Issue-port probe: time (ms) of a loop of packed FFMA2 with na ∈ {0,4,8} independent integer ops per 8 FFMA2. */
-PT_API int pt_probe_ffma2_issue(int device, int na, double *ms_out);
-/* Profiling aid: dog_window45_argmax writes (smid, clock64 at start / after stage / after row pass /
- * after column pass / end) per (video, step) into dev_buf ([n][T][6] int64); NULL switches it off. */
-PT_API int pt_debug_window45_timing(void *dev_buf);
-/* Overwrite `bytes` of device scratch on `stream` (L2 flush between timed repeats). */
-PT_API int pt_flush_l2(void *scratch, size_t bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,6 @@ from .api import (  # noqa: F401
     track_segments,
 )
 from .feeder import FrameFeeder, PinnedArray  # noqa: F401
-from .synth import SyntheticVideo, build_trajectory, make_video, my_partition, render_frame, spiral  # noqa: F401
 from .tracker import (  # noqa: F401
     Tracker,
     TrackerBatch,

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpawsome_cuda.so")
+# PAWSOME_CUDA_LIB: load another build of the same ABI (tools/phase_timing.py loads the -DPT_PROBES build)
+LIB_PATH = os.environ.get("PAWSOME_CUDA_LIB") or os.path.join(_HERE, "libpawsome_cuda.so")
 
 PT_OK = 0
 PT_PIX_U8 = 0
@@ -78,10 +79,7 @@ SIGNATURES = {
     "pt_tracker_step": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _fp]),
     "pt_tracker_step_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int, _ip, _ip, _fp]),
     "pt_tracker_batch": (_vp, [_vp]),
-    "pt_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
-    "pt_probe_ffma2_issue": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
-    "pt_debug_window45_timing": (C.c_int, [_vp]),
-    "pt_flush_l2": (C.c_int, [_vp, C.c_size_t, _vp]),
+    "pt_batch_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "pt_batch_rect_argmax": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _fp]),
     "pt_batch_rect_argmax_all": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _fp, C.c_int]),
 }

@@ -19,6 +19,9 @@
 #include <thread>
 #include <vector>
 
+struct pt_batch;
+static void sync_batch_streams(pt_batch *b);                   // every stream this batch has work on (not the whole device)
+
 namespace {
 
 thread_local std::string g_err = "";
@@ -121,10 +124,10 @@ BufPool &pool() { static BufPool *p = new BufPool(); return *p; }     // never d
 struct PinnedBuf {
     void *p = nullptr;
     size_t cap = 0;
-    int ensure(size_t bytes)
+    int ensure(size_t bytes, pt_batch *owner)
     {
         if (bytes <= cap) return PT_OK;
-        if (p) cudaDeviceSynchronize();                        // regrow: nothing in flight may still use the old buffer
+        if (p) sync_batch_streams(owner);                      // regrow: nothing in flight may still use the old buffer
         release();
         const size_t c = BufPool::round_cap(bytes);
         p = pool().get(-1, c);
@@ -143,10 +146,10 @@ struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     int dev = 0;
-    int ensure(size_t bytes)
+    int ensure(size_t bytes, pt_batch *owner)
     {
         if (bytes <= cap) return PT_OK;
-        if (p) cudaDeviceSynchronize();                        // regrow: nothing in flight may still use the old buffer
+        if (p) sync_batch_streams(owner);                      // regrow: nothing in flight may still use the old buffer
         release();
         const size_t c = BufPool::round_cap(bytes);
         CU(cudaGetDevice(&dev));
@@ -168,9 +171,8 @@ bool alloc_range(const void *p, const char **base, size_t *size)
 {
     typedef CUresult (*attr_fn)(void *, CUpointer_attribute, CUdeviceptr);
     static attr_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void *sym = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &sym, cudaEnableDefault, &q) == cudaSuccess &&
@@ -178,7 +180,7 @@ bool alloc_range(const void *p, const char **base, size_t *size)
             fn = (attr_fn)sym;
         else
             cudaGetLastError();
-    }
+    });
     if (!fn) return false;
     CUdeviceptr start = 0;
     size_t sz = 0;
@@ -187,6 +189,52 @@ bool alloc_range(const void *p, const char **base, size_t *size)
     *base = (const char *)(uintptr_t)start;
     *size = sz;
     return sz > 0;
+}
+
+// Defaults of the per-batch knobs from the PT_* environment variables — read ONCE per process; a batch copies
+// them at creation (pt_batch_set_option changes them per handle).  Nothing on a per-call path calls getenv.
+const pt::Cfg &defaults_from_env()
+{
+    static pt::Cfg cfg;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+        cfg.window45 = getenv("PT_DISABLE_WINDOW45") ? 0 : 1;
+        cfg.rect45 = getenv("PT_DISABLE_RECT45") ? 0 : 1;
+        cfg.rot = geti("PT_W45_ROT", 1);
+        cfg.skew = geti("PT_W45_SKEW", 1);
+        cfg.r45_chunks = std::max(0, geti("PT_R45_CHUNKS", 0));
+        cfg.generic_target = std::max(1, geti("PT_GENERIC_TARGET", 4 * 148));
+        cfg.mode_slow = getenv("PT_MODE_SLOW") ? 1 : 0;
+        cfg.zero_copy = getenv("PT_NO_ZEROCOPY") ? 0 : 1;
+        cfg.host_lanes = std::max(0, geti("PT_HOST_LANES", 0));
+        cfg.cluster = geti("PT_W45_CLUSTER", 0);
+        cfg.bulk = std::min(2, std::max(0, geti("PT_W45_BULK", 2)));
+    });
+    return cfg;
+}
+
+// Per-device one-time setup (dynamic shared memory opt-in of every kernel is a per-device attribute; SM count).
+constexpr int kMaxDevices = 64;
+struct DeviceInfo { bool ready = false; int sms = 0; };
+int device_info(int device, DeviceInfo *out)
+{
+    static std::mutex m;
+    static DeviceInfo info[kMaxDevices];
+    if (device < 0 || device >= kMaxDevices) return fail(PT_ERR_ARG, "device %d out of range", device);
+    std::lock_guard<std::mutex> g(m);
+    DeviceInfo &d = info[device];
+    if (!d.ready) {
+        CU(cudaSetDevice(device));
+        int sms = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        CU(pt::generic_init_device());
+        CU(pt::window45_init_device());
+        d.sms = sms > 0 ? sms : 148;
+        d.ready = true;
+    }
+    *out = d;
+    return PT_OK;
 }
 
 bool is_pinned_or_device(const void *p)
@@ -229,7 +277,8 @@ struct pt_batch {
     std::vector<int32_t> h_guess;
     bool h_guess_valid = false, d_guess_stale = false;
     int center_key[3] = {-1, -1, -1};    // (rr, rc, w) d_center was last filled for
-    bool staging_busy = false;           // an async H2D from the guess staging may be in flight
+    bool staging_busy = false;           // an async H2D from the guess staging may be in flight …
+    cudaStream_t staging_stream = nullptr;   // … on this stream
     int2 *d_center = nullptr;            // crop-mode guess: centre of the footprint
     unsigned long long *d_keys = nullptr;
     unsigned int *d_counters = nullptr;
@@ -253,12 +302,23 @@ struct pt_batch {
     std::vector<pt_lane> lanes;
     long long launches = 0;
     const char *last_kernel = "";        // name of the kernel the most recent launch_step ran
-    bool use45 = false;
+    pt::Cfg cfg;                         // tuning / debugging knobs (defaults_from_env at create, pt_batch_set_option)
+    cudaStream_t ext_stream = nullptr;   // caller stream of the most recent pt_batch_track_device_async (may still run)
+    PinnedBuf h_small;                   // pinned staging for the small synchronous uploads (fills, centres, taps)
 };
 
 struct pt_tracker {
     pt_batch *b = nullptr;
 };
+
+static void sync_batch_streams(pt_batch *b)
+{
+    if (!b) return;
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    if (b->ext_stream) { cudaStreamSynchronize(b->ext_stream); b->ext_stream = nullptr; }
+    for (auto &ln : b->lanes) if (ln.stream) cudaStreamSynchronize(ln.stream);
+}
 
 namespace {
 
@@ -295,14 +355,12 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     return a;
 }
 
-void decompose(pt::WinArgs &a, int nwin)
+void decompose(pt::WinArgs &a, int nwin, int target)
 {
     // Strips of 32 output columns; row chunks only where a launch would otherwise leave the GPU
     // under-occupied.  Each extra chunk repeats 2w footprint rows of the row pass, so chunks are
     // added until ~kTarget CTAs exist (measured best for the 1080p full-frame shape) and never below
     // one batch of rows.
-    static int target = 0;
-    if (target == 0) { const char *e = getenv("PT_GENERIC_TARGET"); target = e ? atoi(e) : 4 * 148; if (target < 1) target = 1; }
     a.strips = (a.wc + pt::kTileCols - 1) / pt::kTileCols;
     const int total = nwin * a.strips;
     int chunks = 1;
@@ -319,20 +377,20 @@ void decompose(pt::WinArgs &a, int nwin)
 // Thread-safe: touches no batch state.
 cudaError_t launch_windows(const pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
 {
-    if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
-        return pt::launch_window45(a, nwin, b->pixel, s);
-    if (b->use45 && pt::rect45_supported(a, b->pixel))
-        return pt::launch_rect45(a, nwin, b->pixel, s);
-    decompose(a, nwin);
+    if (b->cfg.window45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
+        return pt::launch_window45(a, b->cfg, nwin, b->pixel, s);
+    if (b->cfg.window45 && pt::rect45_supported(a, b->cfg, b->pixel))
+        return pt::launch_rect45(a, b->cfg, nwin, b->pixel, s);
+    decompose(a, nwin, b->cfg.generic_target);
     return pt::launch_generic(a, nwin, b->pixel, s);
 }
 
 int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
 {
     const cudaError_t e = launch_windows(b, a, nwin, s);
-    if (b->use45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
-        b->last_kernel = pt::window45_uses_rot(a, nwin) ? pt::window45_rot_name() : pt::window45_name();
-    else if (b->use45 && pt::rect45_supported(a, b->pixel)) b->last_kernel = pt::rect45_name();
+    if (b->cfg.window45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
+        b->last_kernel = pt::window45_kernel_for(a, b->cfg, nwin);
+    else if (b->cfg.window45 && pt::rect45_supported(a, b->cfg, b->pixel)) b->last_kernel = pt::rect45_name();
     else b->last_kernel = b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     b->launches += 1;
@@ -346,17 +404,34 @@ int current_frames(pt_batch *b, const void **base, size_t *stride, size_t *pitch
     return fail(PT_ERR_STATE, "no frame attached: call pt_batch_set_frames or pt_batch_bind_device_frames first");
 }
 
+// Small host → device upload ordered on the batch's own stream: through pinned staging (a pageable cudaMemcpy on the
+// legacy stream may return before the DMA lands and is not ordered against the non-blocking streams the kernels
+// run on), then one stream synchronise so the staging can be reused and every later launch — on any stream — sees it.
+int upload_small(pt_batch *b, void *dst, const void *src, size_t bytes)
+{
+    int rc = b->h_small.ensure(bytes, b);
+    if (rc) return rc;
+    memcpy(b->h_small.p, src, bytes);
+    CU(cudaMemcpyAsync(dst, b->h_small.p, bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return PT_OK;
+}
+
 int upload_guess(pt_batch *b, const int32_t *g, cudaStream_t s)
 {
-    int rc = b->h_out.ensure((size_t)b->n * 32);
+    int rc = b->h_out.ensure((size_t)b->n * 32, b);
     if (rc) return rc;
     // staging region [n*16, n*24) of h_out is reserved for guesses
     int32_t *st = reinterpret_cast<int32_t *>((char *)b->h_out.p + (size_t)b->n * 24);
-    if (b->staging_busy) { CU(cudaStreamSynchronize(s)); b->staging_busy = false; }   // earlier async copy still reading it?
+    if (b->staging_busy) {                                     // an earlier async copy may still be reading the staging
+        CU(cudaStreamSynchronize(b->staging_stream ? b->staging_stream : s));
+        b->staging_busy = false;
+    }
     memcpy(st, g, sizeof(int32_t) * 2 * (size_t)b->n);
     CU(cudaMemcpyAsync(b->d_guess, st, sizeof(int2) * (size_t)b->n, cudaMemcpyHostToDevice, s));
     b->guess_set = true;
     b->staging_busy = true;
+    b->staging_stream = s;
     if (g != b->h_guess.data()) b->h_guess.assign(g, g + 2 * (size_t)b->n);
     b->h_guess_valid = true;
     b->d_guess_stale = false;
@@ -386,7 +461,7 @@ int upload_frames(pt_batch *b, const void *const *frames, size_t pitch, int slot
     const size_t row_bytes = (size_t)b->W * es;
     const size_t src_pitch_b = pitch * es;
     if (pitch < (size_t)b->W) return fail(PT_ERR_ARG, "pitch %zu smaller than W %d", pitch, b->W);
-    int rc = b->d_frames[slot].ensure(b->own_stride * es * (size_t)b->n);
+    int rc = b->d_frames[slot].ensure(b->own_stride * es * (size_t)b->n, b);
     if (rc) return rc;
     char *dbase = (char *)b->d_frames[slot].p;
     const size_t dst_pitch_b = b->own_pitch * es, dst_stride_b = b->own_stride * es;
@@ -408,7 +483,7 @@ int upload_frames(pt_batch *b, const void *const *frames, size_t pitch, int slot
     }
     // pageable source: pack rows into pinned staging (two halves, alternating) then DMA
     const size_t per_half = std::max<size_t>(1, std::min<size_t>((size_t)b->n, (64u << 20) / std::max<size_t>(frame_bytes, 1)));
-    for (int h = 0; h < 2; ++h) { rc = b->h_stage[h].ensure(per_half * frame_bytes); if (rc) return rc; }
+    for (int h = 0; h < 2; ++h) { rc = b->h_stage[h].ensure(per_half * frame_bytes, b); if (rc) return rc; }
     int half = 0;
     for (int v0 = 0; v0 < b->n; v0 += (int)per_half, half ^= 1) {
         const int v1 = std::min(b->n, v0 + (int)per_half);
@@ -431,7 +506,7 @@ int upload_frames(pt_batch *b, const void *const *frames, size_t pitch, int slot
 int read_results(pt_batch *b, int32_t *out_ij, int32_t *out_raw, float *out_resp, cudaStream_t s)
 {
     const size_t n = (size_t)b->n;
-    int rc = b->h_out.ensure(n * 32);
+    int rc = b->h_out.ensure(n * 32, b);
     if (rc) return rc;
     int4 *hp = reinterpret_cast<int4 *>(b->h_out.p);
     float *hr = reinterpret_cast<float *>((char *)b->h_out.p + n * 16);
@@ -505,6 +580,8 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
 
     const int L = kernel_len_of(tw);
     const int Lpad = ((L + pt::kTapChunk - 1) / pt::kTapChunk) * pt::kTapChunk;
+    DeviceInfo dinfo;
+    { const int rc0 = device_info(device, &dinfo); if (rc0) return rc0; }   // once per device: shared-memory opt-ins, SM count
     CU(cudaSetDevice(device));
     int smem_optin = 0;      // (cudaGetDeviceProperties costs ~20 ms per call; one attribute is microseconds)
     CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -516,6 +593,8 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     if (!b) return fail(PT_ERR_NOMEM, "out of host memory");
     b->n = n; b->H = H; b->W = W; b->tw = tw; b->darker = darker != 0; b->pixel = pixel; b->device = device;
     b->L = L; b->w = L / 2; b->Lpad = Lpad;
+    b->cfg = defaults_from_env();
+    b->cfg.sms = dinfo.sms;
     configure_window(b, ws_rows, ws_cols);
     b->own_pitch = pixel == PT_PIX_U8 ? (((size_t)W + 15) & ~(size_t)15) : (((size_t)W + 3) & ~(size_t)3);
     b->own_stride = b->own_pitch * (size_t)H;
@@ -551,7 +630,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
         const size_t o_hist = take(sizeof(unsigned int) * pt::kModeScratch * (size_t)n);
         const size_t o_pos = take(sizeof(int4) * n), o_resp = take(sizeof(float) * n);
         const size_t o_xflag = take(sizeof(unsigned int) * n), o_xpos = take(sizeof(int2) * n);
-        if (rc == PT_OK && b->d_arena.ensure(off) != PT_OK) rc = PT_ERR_CUDA;
+        if (rc == PT_OK && b->d_arena.ensure(off, b) != PT_OK) rc = PT_ERR_CUDA;
         if (rc == PT_OK) {
             char *a0 = (char *)b->d_arena.p;
             b->d_taps_row = (float2 *)(a0 + o_trow); b->d_taps_col = (float2 *)(a0 + o_tcol);
@@ -560,14 +639,14 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
             b->d_keys = (unsigned long long *)(a0 + o_keys); b->d_counters = (unsigned int *)(a0 + o_cnt);
             b->d_hist = (unsigned int *)(a0 + o_hist); b->d_pos = (int4 *)(a0 + o_pos); b->d_resp = (float *)(a0 + o_resp);
             b->d_xflag = (unsigned int *)(a0 + o_xflag); b->d_xpos = (int2 *)(a0 + o_xpos);
-            cu(cudaMemset(b->d_arena.p, 0, off), "memset");
-            cu(cudaMemcpy(b->d_taps_row, trow.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
-            cu(cudaMemcpy(b->d_taps_col, tcol.data(), sizeof(float2) * Lpad, cudaMemcpyHostToDevice), "taps upload");
+            cu(cudaMemsetAsync(b->d_arena.p, 0, off, b->stream), "memset");
+            // taps: d_taps_row and d_taps_col are adjacent arena slots of equal padded size → one staged upload each
+            if (rc == PT_OK && upload_small(b, b->d_taps_row, trow.data(), sizeof(float2) * Lpad) != PT_OK) rc = PT_ERR_CUDA;
+            if (rc == PT_OK && upload_small(b, b->d_taps_col, tcol.data(), sizeof(float2) * Lpad) != PT_OK) rc = PT_ERR_CUDA;
         }
     }
     if (rc != PT_OK) { pt_batch_destroy(b); return rc; }
     b->h_fill.assign(n, 0);
-    b->use45 = getenv("PT_DISABLE_WINDOW45") == nullptr;   // debugging/parity knob: force the generic kernel
     *out = b;
     return PT_OK;
 }
@@ -576,12 +655,12 @@ void pt_batch_destroy(pt_batch *b)
 {
     if (!b) return;
     cudaSetDevice(b->device);
-    if (b->stream) cudaStreamSynchronize(b->stream);
-    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    sync_batch_streams(b);               // incl. a caller stream handed to pt_batch_track_device_async
     for (auto &ln : b->lanes) {
-        if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
+        if (ln.stream) cudaStreamDestroy(ln.stream);
         ln.h_crops.release(); ln.h_res.release(); ln.d_crops.release();
     }
+    b->h_small.release();
     b->d_arena.release();
     for (int i = 0; i < 2; ++i) {
         b->d_frames[i].release(); b->h_stage[i].release();
@@ -610,6 +689,7 @@ int pt_batch_set_frames(pt_batch *b, const void *const *frames, size_t pitch)
     int rc = set_device(b);
     if (rc) return rc;
     // make sure no step still reads the slot we are about to overwrite
+    if (b->ext_stream) { CU(cudaStreamSynchronize(b->ext_stream)); b->ext_stream = nullptr; }
     CU(cudaStreamSynchronize(b->stream));
     rc = upload_frames(b, frames, pitch, b->cur_slot, b->stream);
     if (rc) return rc;
@@ -635,7 +715,7 @@ int pt_batch_compute_fill(pt_batch *b, int *fills_out)
     rc = current_frames(b, &base, &stride, &pitch);
     if (rc) return rc;
     cudaError_t e = pt::launch_mode(base, stride, (int)pitch, b->H, b->W, b->n, b->pixel, b->d_hist,
-                                    b->d_fill, b->d_fill_i, b->stream);
+                                    b->d_fill, b->d_fill_i, b->cfg.mode_slow != 0, b->stream);
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "mode kernel launch failed: %s", cudaGetErrorString(e));
     b->launches += 2;
     CU(cudaMemcpyAsync(b->h_fill.data(), b->d_fill_i, sizeof(int) * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
@@ -656,9 +736,9 @@ int pt_batch_set_fill(pt_batch *b, const int *fills)
         b->h_fill[v] = fills[v];
         f[v] = b->pixel == PT_PIX_U8 ? (float)fills[v] : (float)fills[v] / 255.0f;
     }
-    CU(cudaStreamSynchronize(b->stream));
-    CU(cudaMemcpy(b->d_fill, f.data(), sizeof(float) * (size_t)b->n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(b->d_fill_i, b->h_fill.data(), sizeof(int) * (size_t)b->n, cudaMemcpyHostToDevice));
+    sync_batch_streams(b);               // no step on any of the batch's streams may still read the old fills
+    rc = upload_small(b, b->d_fill, f.data(), sizeof(float) * (size_t)b->n); if (rc) return rc;
+    rc = upload_small(b, b->d_fill_i, b->h_fill.data(), sizeof(int) * (size_t)b->n); if (rc) return rc;
     b->fill_set = true;
     return PT_OK;
 }
@@ -710,16 +790,26 @@ int pt_batch_track_device_async(pt_batch *b, const void *dev_base, size_t step_s
     if (rc) return rc;
     if (!b->fill_set) return fail(PT_ERR_STATE, "fill value not set");
     if (!b->guess_set) return fail(PT_ERR_STATE, "no guess on the device: call pt_batch_set_guess");
-    rc = b->d_traj_pos.ensure(sizeof(int4) * (size_t)b->n * T); if (rc) return rc;
-    rc = b->d_traj_resp.ensure(sizeof(float) * (size_t)b->n * T); if (rc) return rc;
+    rc = b->d_traj_pos.ensure(sizeof(int4) * (size_t)b->n * T, b); if (rc) return rc;
+    rc = b->d_traj_resp.ensure(sizeof(float) * (size_t)b->n * T, b); if (rc) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : b->stream;
+    if (s != b->stream) {
+        // A batch runs on one stream at a time: work of earlier calls (own stream or another caller stream) is
+        // finished before this one is enqueued, and the caller stream is remembered so that destroy / regrow /
+        // pt_batch_read_track can wait for it.
+        sync_batch_streams(b);
+        b->ext_stream = s;
+    } else if (b->ext_stream) {
+        CU(cudaStreamSynchronize(b->ext_stream));
+        b->ext_stream = nullptr;
+    }
     rc = flush_guess(b, s); if (rc) return rc;
     b->h_guess_valid = false;                 // the chain advances on the device only
     const size_t es = px_size(b->pixel);
     {
         // the specialised kernel chains all T steps inside one launch (one CTA per video)
         pt::WinArgs a = make_args(b, dev_base, frame_stride, pitch, b->H, b->W, b->d_guess, b->n);
-        if (b->use45 && pt::window45_supported(a, b->pixel)) {   // (the 4-CTA kernel covers a subset of this)
+        if (b->cfg.window45 && pt::window45_supported(a, b->pixel)) {
             a.next_guess = b->d_guess;
             a.traj_pos = (int4 *)b->d_traj_pos.p; a.traj_resp = (float *)b->d_traj_resp.p;
             a.T = T; a.step_stride = step_stride;
@@ -745,13 +835,17 @@ int pt_batch_read_track(pt_batch *b, int T, int32_t *out_ij, float *out_resp)
     if (rc) return rc;
     const size_t cnt = (size_t)b->n * T;
     if (b->d_traj_pos.cap < cnt * sizeof(int4)) return fail(PT_ERR_STATE, "no trajectory of %d steps on the device", T);
-    rc = b->h_out.ensure(std::max<size_t>(cnt * 20, (size_t)b->n * 32));
+    rc = b->h_out.ensure(std::max<size_t>(cnt * 20, (size_t)b->n * 32), b);
     if (rc) return rc;
     int4 *hp = (int4 *)b->h_out.p;
     float *hr = (float *)((char *)b->h_out.p + cnt * 16);
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(hp, b->d_traj_pos.p, cnt * 16, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(hr, b->d_traj_resp.p, cnt * 4, cudaMemcpyDeviceToHost));
+    // only this batch's streams are waited for (other handles keep running); pinned destination → true async copies
+    cudaStream_t s = b->ext_stream ? b->ext_stream : b->stream;
+    CU(cudaMemcpyAsync(hp, b->d_traj_pos.p, cnt * 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hr, b->d_traj_resp.p, cnt * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    b->ext_stream = nullptr;
+    b->staging_busy = false;
     for (size_t i = 0; i < cnt; ++i) {
         if (out_ij) { out_ij[2 * i] = hp[i].x; out_ij[2 * i + 1] = hp[i].y; }
         if (out_resp) out_resp[i] = hr[i];
@@ -863,7 +957,7 @@ int ensure_lanes(pt_batch *b)
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 4;
     int want = (int)std::min<unsigned>(std::min<unsigned>(hw, 16u), (unsigned)b->n);
-    if (const char *env = getenv("PT_HOST_LANES")) { int k = atoi(env); if (k >= 1) want = std::min(k, b->n); }
+    if (b->cfg.host_lanes >= 1) want = std::min(b->cfg.host_lanes, b->n);
     if ((int)b->lanes.size() != want) {
         for (auto &ln : b->lanes) { if (ln.stream) cudaStreamDestroy(ln.stream); ln.h_crops.release(); ln.h_res.release(); ln.d_crops.release(); }
         b->lanes.assign(want, pt_lane());
@@ -879,13 +973,14 @@ int ensure_lanes(pt_batch *b)
     const size_t cp = b->pixel == PT_PIX_U8 ? (((size_t)fc + 15) & ~(size_t)15) : (((size_t)fc + 3) & ~(size_t)3);
     for (auto &ln : b->lanes) {
         const size_t nl = (size_t)(ln.v1 - ln.v0);
-        int rc = ln.h_crops.ensure(cp * fr * es * nl); if (rc) return rc;
-        rc = ln.d_crops.ensure(cp * fr * es * nl); if (rc) return rc;
-        rc = ln.h_res.ensure(nl * 20); if (rc) return rc;
+        int rc = ln.h_crops.ensure(cp * fr * es * nl, b); if (rc) return rc;
+        rc = ln.d_crops.ensure(cp * fr * es * nl, b); if (rc) return rc;
+        rc = ln.h_res.ensure(nl * 20, b); if (rc) return rc;
     }
     if (b->center_key[0] != b->rr || b->center_key[1] != b->rc || b->center_key[2] != b->w) {
         std::vector<int2> c(b->n, make_int2(b->rr + b->w + 1, b->rc + b->w + 1));
-        CU(cudaMemcpy(b->d_center, c.data(), sizeof(int2) * (size_t)b->n, cudaMemcpyHostToDevice));
+        int rc = upload_small(b, b->d_center, c.data(), sizeof(int2) * (size_t)b->n);   // complete before any lane stream starts
+        if (rc) return rc;
         b->center_key[0] = b->rr; b->center_key[1] = b->rc; b->center_key[2] = b->w;
     }
     return PT_OK;
@@ -940,35 +1035,40 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
     // the geometry dispatches to the chained kernel, the kernel reads each window's footprint straight
     // from the host frame over PCIe and writes every step's result straight into pinned host memory —
     // the whole frame loop (:163-169) is one launch, with no host gather and no per-step round trip.
-    if (!getenv("PT_NO_ZEROCOPY")) {
+    if (b->cfg.zero_copy) {
         pt::WinArgs probe = make_args(b, nullptr, 0, pitch, b->H, b->W, b->d_guess, b->n);
         probe.frame_ptrs = reinterpret_cast<const void *const *>(1);   // "pointer table" marker for the support check
-        bool ok = b->use45 && pt::window45_supported(probe, b->pixel);
+        bool ok = b->cfg.window45 && pt::window45_supported(probe, b->pixel);
+        const size_t frame_bytes = ((size_t)(b->H - 1) * pitch + (size_t)b->W) * px_size(b->pixel);   // first to last byte of a frame
         const size_t cnt = n * (size_t)T;
-        if (ok) { rc = b->h_ptrs.ensure(cnt * sizeof(void *)); if (rc) return rc; }
+        if (ok) { rc = b->h_ptrs.ensure(cnt * sizeof(void *), b); if (rc) return rc; }
         const void **hp = (const void **)b->h_ptrs.p;
         // host address range [rb, rb+rs) already known to be pinned, and its device alias rd
         const char *rb = nullptr, *rd = nullptr; size_t rs = 0;
         for (size_t i = 0; ok && i < cnt; ++i) {
             const char *f = (const char *)frames[i];
             if (!f) return fail(PT_ERR_ARG, "frames[%zu] is NULL", i);
-            if (!(rb && f >= rb && f < rb + rs)) {
+            if (!(rb && f >= rb && f + frame_bytes <= rb + rs)) {
                 cudaPointerAttributes at;
                 if (cudaPointerGetAttributes(&at, f) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
                 if (at.type != cudaMemoryTypeHost || !at.devicePointer) { ok = false; break; }
                 const char *base = nullptr; size_t size = 0;
-                if (alloc_range(f, &base, &size) && f >= base && f < base + size) {
+                if (alloc_range(f, &base, &size) && f >= base && f + frame_bytes <= base + size) {
                     rb = base; rs = size; rd = (const char *)at.devicePointer - (f - base);
                 } else {
-                    rb = f; rs = 1; rd = (const char *)at.devicePointer;      // this pointer only
+                    // allocation range unknown (or the frame would run past it): check the frame's last byte too
+                    cudaPointerAttributes at2;
+                    if (cudaPointerGetAttributes(&at2, f + frame_bytes - 1) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+                    if (at2.type != cudaMemoryTypeHost || !at2.devicePointer) { ok = false; break; }
+                    rb = f; rs = frame_bytes; rd = (const char *)at.devicePointer;      // this frame only
                 }
             }
             hp[i] = rd + (f - rb);
             if (b->pixel == PT_PIX_U8 && ((uintptr_t)hp[i] & 3u) != 0) { ok = false; break; }
         }
         if (ok) {
-            rc = b->d_ptrs.ensure(cnt * sizeof(void *)); if (rc) return rc;
-            rc = b->h_traj.ensure(cnt * 20); if (rc) return rc;
+            rc = b->d_ptrs.ensure(cnt * sizeof(void *), b); if (rc) return rc;
+            rc = b->h_traj.ensure(cnt * 20, b); if (rc) return rc;
             int4 *hpos = (int4 *)b->h_traj.p;
             float *hresp = (float *)((char *)b->h_traj.p + cnt * 16);
             rc = flush_guess(b); if (rc) return rc;
@@ -991,6 +1091,7 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
     rc = ensure_lanes(b); if (rc) return rc;
     HostTrack ht;
     ht.b = b; ht.frames = frames; ht.T = T; ht.pitch = pitch; ht.out_ij = out_ij; ht.out_resp = out_resp;
+    if (b->ext_stream) { CU(cudaStreamSynchronize(b->ext_stream)); b->ext_stream = nullptr; }
     CU(cudaStreamSynchronize(b->stream));          // fill values / centres / earlier steps are complete
     b->staging_busy = false;
     if (b->h_guess_valid) ht.guess = b->h_guess;
@@ -1022,7 +1123,7 @@ int pt_batch_response_map(pt_batch *b, int v, int gi, int gj, float *out_map)
     const void *base; size_t stride, pitch;
     rc = current_frames(b, &base, &stride, &pitch); if (rc) return rc;
     const size_t cnt = (size_t)b->wr * b->wc;
-    rc = b->d_map.ensure(cnt * 4); if (rc) return rc;
+    rc = b->d_map.ensure(cnt * 4, b); if (rc) return rc;
     const size_t es = px_size(b->pixel);
     pt::WinArgs a = make_args(b, (const char *)base + (size_t)v * stride * es, stride, pitch, b->H, b->W, nullptr, 1);
     a.rect_mode = 1; a.ry0 = gi - 1 - b->rr; a.rx0 = gj - 1 - b->rc;
@@ -1053,7 +1154,7 @@ int pt_batch_rect_argmax(pt_batch *b, int v, int y0, int x0, int wr, int wc,
     a.fill = b->d_fill + v; a.keys = b->d_keys + v; a.counters = b->d_counters + v; a.tickets = b->d_counters + b->n + 2 * v;
     a.out_pos = b->d_pos + v; a.out_resp = b->d_resp + v;
     rc = launch_step(b, a, 1, b->stream); if (rc) return rc;
-    rc = b->h_out.ensure((size_t)b->n * 32); if (rc) return rc;
+    rc = b->h_out.ensure((size_t)b->n * 32, b); if (rc) return rc;
     int4 *hp = reinterpret_cast<int4 *>(b->h_out.p);                 // pinned: truly asynchronous copies
     float *hr = reinterpret_cast<float *>((char *)b->h_out.p + 16);
     CU(cudaMemcpyAsync(hp, b->d_pos + v, sizeof(int4), cudaMemcpyDeviceToHost, b->stream));
@@ -1079,7 +1180,7 @@ int pt_batch_rect_argmax_all(pt_batch *b, int y0, int x0, int wr, int wc, int32_
     a.rect_mode = 1; a.ry0 = y0; a.rx0 = x0; a.wr = wr; a.wc = wc;
     rc = launch_step(b, a, b->n, b->stream); if (rc) return rc;
     if (no_readback) return PT_OK;
-    rc = b->h_out.ensure((size_t)b->n * 32); if (rc) return rc;
+    rc = b->h_out.ensure((size_t)b->n * 32, b); if (rc) return rc;
     int4 *hp = reinterpret_cast<int4 *>(b->h_out.p);
     float *hr = reinterpret_cast<float *>((char *)b->h_out.p + (size_t)b->n * 16);
     CU(cudaMemcpyAsync(hp, b->d_pos, (size_t)b->n * sizeof(int4), cudaMemcpyDeviceToHost, b->stream));
@@ -1093,6 +1194,29 @@ int pt_batch_rect_argmax_all(pt_batch *b, int y0, int x0, int wr, int wc, int32_
     return PT_OK;
 }
 
+int pt_batch_set_option(pt_batch *b, const char *name, int value)
+{
+    if (!b || !name) return fail(PT_ERR_ARG, "NULL argument");
+    struct Opt { const char *name; int pt::Cfg::* field; int lo, hi; };
+    static const Opt opts[] = {
+        {"window45", &pt::Cfg::window45, 0, 1},       {"rect45", &pt::Cfg::rect45, 0, 1},
+        {"rot", &pt::Cfg::rot, 0, 2},                 {"skew", &pt::Cfg::skew, 0, 2},
+        {"r45_chunks", &pt::Cfg::r45_chunks, 0, 1 << 20}, {"generic_target", &pt::Cfg::generic_target, 1, 1 << 20},
+        {"mode_slow", &pt::Cfg::mode_slow, 0, 1},     {"zero_copy", &pt::Cfg::zero_copy, 0, 1},
+        {"host_lanes", &pt::Cfg::host_lanes, 0, 1024}, {"cluster", &pt::Cfg::cluster, 0, 8},
+        {"bulk", &pt::Cfg::bulk, 0, 2},
+    };
+    for (const Opt &o : opts) {
+        if (strcmp(o.name, name) != 0) continue;
+        if (value < o.lo || value > o.hi) return fail(PT_ERR_ARG, "option %s: value %d outside %d..%d", name, value, o.lo, o.hi);
+        if (o.field == &pt::Cfg::cluster && !(value == 0 || value == 1 || value == 2 || value == 4 || value == 8))
+            return fail(PT_ERR_ARG, "option cluster: 0 (auto), 1 (off), 2, 4 or 8 CTAs per window");
+        b->cfg.*(o.field) = value;
+        return PT_OK;
+    }
+    return fail(PT_ERR_ARG, "unknown option '%s'", name);
+}
+
 long long pt_batch_launch_count(const pt_batch *b) { return b ? b->launches : 0; }
 
 const char *pt_batch_kernel_name(const pt_batch *b)
@@ -1101,8 +1225,8 @@ const char *pt_batch_kernel_name(const pt_batch *b)
     pt::WinArgs a;
     memset(&a, 0, sizeof a);
     a.wr = b->wr; a.wc = b->wc; a.L = b->L; a.w = b->w; a.h_taps = b->h_taps.data();
-    if (b->use45 && pt::window45_supported(a, b->pixel)) return pt::window45_name();
-    if (b->use45 && a.L == 65 && !getenv("PT_DISABLE_RECT45") && (long long)a.wr * a.wc >= 24 * 24) return pt::rect45_name();
+    if (b->cfg.window45 && pt::window45_supported(a, b->pixel)) return pt::window45_name();
+    if (b->cfg.window45 && b->cfg.rect45 && a.L == 65 && (long long)a.wr * a.wc >= 24 * 24) return pt::rect45_name();
     return b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
 }
 
@@ -1115,7 +1239,7 @@ int pt_batch_downscale(pt_batch *b, int out_h, int out_w, uint8_t *out)
     const void *base; size_t stride, pitch;
     rc = current_frames(b, &base, &stride, &pitch); if (rc) return rc;
     const size_t bytes = (size_t)b->n * out_h * out_w;
-    rc = b->d_map.ensure(bytes); if (rc) return rc;
+    rc = b->d_map.ensure(bytes, b); if (rc) return rc;
     cudaError_t e = pt::launch_downscale(base, stride, (int)pitch, b->H, b->W, b->n, b->pixel, out_h, out_w,
                                          (uint8_t *)b->d_map.p, b->stream);
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -1139,6 +1263,15 @@ int pt_host_free(void *p)
 }
 
 const char *pt_batch_last_kernel(const pt_batch *b) { return b ? b->last_kernel : ""; }
+
+#ifdef PT_PROBES
+// Profiling build only (libpawsome_cuda_probes.so): phase timestamps of the window45 kernels → dev_buf [n][T][6] int64.
+PT_API int pt_debug_window45_timing(void *dev_buf)
+{
+    pt::window45_set_debug((long long *)dev_buf);
+    return PT_OK;
+}
+#endif
 
 void *pt_batch_stream(const pt_batch *b) { return b ? (void *)b->stream : nullptr; }
 

@@ -1,10 +1,9 @@
-// pt_bench.cu — measurement helpers exported for bench.py: the FP32 FMA peak
-// of the device (the denominator of the FP32-pipe roofline; SURVEY §8d asks
-// for a measured value instead of the nominal 148×128×2×clock) and an L2 flush.
-#include "../../include/pawsome.h"
+// pt_bench.cu — libpawsome_bench.so (include/pawsome_bench.h): measurement helpers for bench.py / tools/, kept OUT
+// of the product library: the FP32 FMA peak of the device (the denominator of the FP32-pipe roofline; SURVEY §8d
+// asks for a measured value instead of the nominal 148×128×2×clock), an issue-port probe and an L2 flush.
+#include "../../include/pawsome_bench.h"
 #include <cuda_runtime.h>
 #include <cstdio>
-#include "pt_kernels.cuh"
 
 namespace {
 
@@ -47,6 +46,37 @@ __global__ void __launch_bounds__(256) fma_peak_packed(float *out, int iters, fl
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(av), "l"(bv));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        s += lo + hi;
+    }
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Packed FP32 add (add.rn.f32x2): 64 lane-adds per issued instruction.  If this ran at the issue rate of a scalar
+// FADD, folding the symmetric row taps with packed adds would halve their issue slots; measured it does not
+// (it occupies the pipe for two cycles, like FFMA2).
+__global__ void __launch_bounds__(256) fadd_peak_packed(float *out, int iters, float a)
+{
+    unsigned long long acc[8];
+    unsigned long long av;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float x = (float)(threadIdx.x + i);
+        asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(x), "f"(x + 0.5f));
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[i]) : "l"(av));
         }
     }
     float s = 0.f;
@@ -110,46 +140,48 @@ extern "C" {
 
 // Measures FP32 FMA throughput (TFLOP/s, 2 flops per FMA). packed=0: scalar
 // FFMA; packed=1: fma.rn.f32x2.  Best of `reps` timed launches.
-PT_API int pt_measure_fp32_peak(int device, int packed, int reps, double *tflops)
+PTB_API int ptb_measure_fp32_peak(int device, int packed, int reps, double *tflops)
 {
-    if (!tflops) return PT_ERR_ARG;
-    if (cudaSetDevice(device) != cudaSuccess) return PT_ERR_CUDA;
+    if (!tflops) return -1;
+    if (cudaSetDevice(device) != cudaSuccess) return -2;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PT_ERR_CUDA;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -2;
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
     float *out = nullptr;
-    if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return PT_ERR_CUDA;
+    if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return -2;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best = 0.0;
     for (int r = 0; r < reps + 2; ++r) {
         cudaEventRecord(e0);
-        if (packed) fma_peak_packed<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        if (packed == 2) fadd_peak_packed<<<blocks, threads>>>(out, iters, 0.001f);
+        else if (packed) fma_peak_packed<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
         else fma_peak_scalar<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
         cudaEventRecord(e1);
-        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return PT_ERR_CUDA; }
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return -2; }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double fl = 2.0 * 16.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+        // per thread and iteration: 16 x 8 lane-FMAs (2 flops each) — or 16 x 8 lane-adds (1 flop each) for packed == 2
+        const double fl = (packed == 2 ? 1.0 : 2.0) * 16.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
         const double tf = fl / (ms * 1e-3) / 1e12;
         if (r >= 2 && tf > best) best = tf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(out);
     *tflops = best;
-    return PT_OK;
+    return 0;
 }
 
 // Issue-port probe (see ffma2_alu_mix): returns ms per launch for na ∈ {0, 4, 8} ALU ops per 8 FFMA2.
-PT_API int pt_probe_ffma2_issue(int device, int na, double *ms_out)
+PTB_API int ptb_probe_ffma2_issue(int device, int na, double *ms_out)
 {
-    if (!ms_out) return PT_ERR_ARG;
-    if (cudaSetDevice(device) != cudaSuccess) return PT_ERR_CUDA;
+    if (!ms_out) return -1;
+    if (cudaSetDevice(device) != cudaSuccess) return -2;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PT_ERR_CUDA;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -2;
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
     float *out = nullptr;
-    if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return PT_ERR_CUDA;
+    if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return -2;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best = 1e30;
@@ -159,7 +191,7 @@ PT_API int pt_probe_ffma2_issue(int device, int na, double *ms_out)
         else if (na == 4) ffma2_alu_mix<4><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
         else ffma2_alu_mix<8><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
         cudaEventRecord(e1);
-        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return PT_ERR_CUDA; }
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return -2; }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         if (r >= 1 && ms < best) best = ms;
@@ -167,22 +199,15 @@ PT_API int pt_probe_ffma2_issue(int device, int na, double *ms_out)
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(out);
     *ms_out = best;
-    return PT_OK;
-}
-
-// Profiling aid: phase timestamps of dog_window45_argmax go to dev_buf ([n][T][6] int64), NULL = off.
-PT_API int pt_debug_window45_timing(void *dev_buf)
-{
-    pt::window45_set_debug((long long *)dev_buf);
-    return PT_OK;
+    return 0;
 }
 
 // Overwrites `bytes` of scratch on `stream` so nothing useful stays in L2.
-PT_API int pt_flush_l2(void *scratch, size_t bytes, void *stream)
+PTB_API int ptb_flush_l2(void *scratch, size_t bytes, void *stream)
 {
-    if (!scratch || bytes < 16) return PT_ERR_ARG;
+    if (!scratch || bytes < 16) return -1;
     flush_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>((float4 *)scratch, bytes / 16);
-    return cudaGetLastError() == cudaSuccess ? PT_OK : PT_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 } // extern "C"

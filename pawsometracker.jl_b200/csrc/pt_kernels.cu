@@ -353,18 +353,26 @@ size_t generic_smem_bytes(int L, int Lpad)
            (size_t)kBatchRows * PIN * sizeof(float);
 }
 
+// cudaFuncSetAttribute is per device: opt both instantiations in to the largest dynamic shared memory the device
+// allows, once per device (pt_batch_create refuses kernel lengths whose footprint exceeds it).
+cudaError_t generic_init_device()
+{
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dog_rect_argmax_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(dog_rect_argmax_generic<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+}
+
 cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s)
 {
     const size_t smem = generic_smem_bytes(a.L, a.Lpad);
     dim3 grid((unsigned)a.strips, (unsigned)a.chunks, (unsigned)n);
-    cudaError_t e;
-    if (pixel == 0) {
-        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect_argmax_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-        dog_rect_argmax_generic<uint8_t><<<grid, kGenericThreads, smem, s>>>(a);
-    } else {
-        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect_argmax_generic<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-        dog_rect_argmax_generic<float><<<grid, kGenericThreads, smem, s>>>(a);
-    }
+    if (pixel == 0) dog_rect_argmax_generic<uint8_t><<<grid, kGenericThreads, smem, s>>>(a);
+    else dog_rect_argmax_generic<float><<<grid, kGenericThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -590,12 +598,12 @@ mode_pick_kernel(unsigned int *hist, int pixel, float *fill_out, int *fill_int_o
 
 cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int H, int W, int n,
                         int pixel, unsigned int *hist, float *fill_out, int *fill_int_out,
-                        cudaStream_t s)
+                        bool force_slow, cudaStream_t s)
 {
     dim3 grid(kModeSplit, (unsigned)n);
     const size_t es = pixel == 0 ? 1 : 4;
     // the vector path needs 16-byte aligned rows that can be read up to the next multiple of 16 bytes
-    const bool vec = !getenv("PT_MODE_SLOW") && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 && ((size_t)pitch * es) % 16 == 0 &&
+    const bool vec = !force_slow && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 && ((size_t)pitch * es) % 16 == 0 &&
                      (frame_stride * es) % 16 == 0 && (size_t)pitch * es >= (((size_t)W * es + 15) & ~(size_t)15);
     cudaError_t e;
     if (vec) {

@@ -11,6 +11,24 @@ constexpr int kBatchRows = 32;   // footprint rows staged per batch (generic ker
 constexpr int kTapChunk = 5;     // taps per unrolled chunk; l = 4⌈σ√2⌉+1 ≡ 1 (mod 4), 65 and 245 divide by 5
 constexpr int kGenericThreads = 128;
 
+// Per-batch tuning / debugging knobs.  Defaults come from the PT_* environment variables, read ONCE per
+// process (defaults_from_env in pt_api.cu); a batch copies them at creation and pt_batch_set_option changes
+// them per handle.  Nothing on a per-call path calls getenv.
+struct Cfg {
+    int sms = 148;            // SM count of the batch's device (cudaDevAttrMultiProcessorCount at create)
+    int window45 = 1;         // 0: never use the l = 65 / 45x45 specialised kernels   (PT_DISABLE_WINDOW45)
+    int rect45 = 1;           // 0: never use dog_rect45_march                          (PT_DISABLE_RECT45)
+    int rot = 1;              // dog_window45_rot: 0 off, 1 where it pays, 2 always     (PT_W45_ROT)
+    int skew = 1;             // two-window CTAs: 0 free-running, 1 token, 2 lock       (PT_W45_SKEW)
+    int r45_chunks = 0;       // chunks per strip of dog_rect45_march, 0 = cost model   (PT_R45_CHUNKS)
+    int generic_target = 592; // CTAs the generic kernel aims for                       (PT_GENERIC_TARGET)
+    int mode_slow = 0;        // 1: always run the last-position pass of mode           (PT_MODE_SLOW)
+    int zero_copy = 1;        // 0: never read pinned host frames in place              (PT_NO_ZEROCOPY)
+    int host_lanes = 0;       // host threads of the pageable footprint path, 0 = auto  (PT_HOST_LANES)
+    int cluster = 0;          // lone-window cluster kernel: 0 auto, 1 off, 2/4/8 CTAs per window (PT_W45_CLUSTER)
+    int bulk = 2;             // cluster kernel staging: 0 global loads, 1 cp.async.bulk per row, 2 one TMA tile copy (PT_W45_BULK)
+};
+
 // One launch = one (trckr::Tracker)(guess) evaluation for every window of the
 // batch (reference: src/PawsomeTracker.jl:55-62).
 struct WinArgs {
@@ -87,21 +105,27 @@ __device__ __forceinline__ void publish_result(const WinArgs &a, int v, unsigned
     if (a.traj_pos) { a.traj_pos[v] = p; a.traj_resp[v] = resp; }
 }
 
+// Per-device one-time setup (cudaFuncSetAttribute is per device): called by pt_batch_create under a lock,
+// once per (process, device), with that device current.
+cudaError_t generic_init_device();
+cudaError_t window45_init_device();
+
 size_t generic_smem_bytes(int L, int Lpad);
 cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s);
 
 // Specialised batched kernel: l = 65 (target_width 25), 45×45 window.
 bool window45_supported(const WinArgs &a, int pixel);
-cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s);
+cudaError_t launch_window45(const WinArgs &a, const Cfg &cfg, int n, int pixel, cudaStream_t s);
+// name of the kernel launch_window45 would run for this launch (dog_window45_argmax / _rot / _cluster<C>)
+const char *window45_kernel_for(const WinArgs &a, const Cfg &cfg, int n);
 const char *window45_name();
-bool window45_uses_rot(const WinArgs &a, int n);   // launch_window45 would run dog_window45_rot for this launch
-const char *window45_rot_name();
-void window45_set_debug(long long *dev_buf);
-long long *window45_debug_ptr();   // phase-timestamp buffer [n][T][6] (profiling aid), nullptr = off
+#ifdef PT_PROBES
+void window45_set_debug(long long *dev_buf);   // phase-timestamp buffer [n][T][6] (profiling build only)
+#endif
 
 // l = 65 rectangles of any size cut into 45x45 tiles evaluated like windows (auto-detect, full frame, …).
-bool rect45_supported(const WinArgs &a, int pixel);
-cudaError_t launch_rect45(const WinArgs &a, int n, int pixel, cudaStream_t s);
+bool rect45_supported(const WinArgs &a, const Cfg &cfg, int pixel);
+cudaError_t launch_rect45(const WinArgs &a, const Cfg &cfg, int n, int pixel, cudaStream_t s);
 const char *rect45_name();
 
 // fillvalue = mode(frame) (src/PawsomeTracker.jl:47) for n frames.
@@ -109,7 +133,7 @@ const char *rect45_name();
 constexpr int kModeScratch = 832;
 cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int H, int W, int n,
                         int pixel, unsigned int *hist, float *fill_out, int *fill_int_out,
-                        cudaStream_t s);
+                        bool force_slow, cudaStream_t s);
 
 // imresize!(dia.buffer, img) (src/diagnose.jl:33): current frame of n videos → [n][oh][ow] u8, bilinear, centre-aligned.
 cudaError_t launch_downscale(const void *frames, size_t frame_stride, int pitch, int H, int W, int n, int pixel,

@@ -32,8 +32,12 @@
 // are fully unrolled, so no tap is ever loaded inside the passes.
 #include "pt_kernels.cuh"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 namespace pt {
 
@@ -84,10 +88,32 @@ struct Args45 {
     int2 *next_guess;                   // [n] or null
     int4 *traj_pos; float *traj_resp;   // [T][n] or null
     int skew;                           // 1: alternate the row passes of the two windows of a CTA (token); 2: lock
+    int tm_rows_step, tm_rows_frame;    // dog_window45_cluster, TMA tensor mode: rows of the 2-D frame tensor per step / per video
     unsigned int *xflag;                // [n] hand-off flags of dog_window45_rot (zero between launches)
     int2 *xpos;                         // [n] hand-off guesses
+#ifdef PT_PROBES
     long long *dbg;                     // optional [n][T][6]: smid|globaltimer, clock64 at start / stage / row / col / end
+#endif
 };
+
+// Phase probes exist only in the profiling build (-DPT_PROBES → libpawsome_cuda_probes.so, tools/phase_timing.py);
+// the product kernels carry none.
+#ifdef PT_PROBES
+#define PT_PROBE_BEGIN(a, v, t, tid)                                                              \
+    long long *dbg = (a).dbg ? (a).dbg + ((size_t)(v) * (a).T + (t)) * 6 : nullptr;                \
+    if (dbg && (tid) == 0) {                                                                      \
+        unsigned int smid_;                                                                       \
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));                                        \
+        unsigned long long gt_;                                                                   \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                   \
+        dbg[0] = ((long long)gt_ << 8) | (long long)(smid_ & 0xFF);                               \
+        dbg[1] = clock64();                                                                       \
+    }
+#define PT_PROBE(k, tid) do { if (dbg && (tid) == 0) dbg[k] = clock64(); } while (0)
+#else
+#define PT_PROBE_BEGIN(a, v, t, tid)
+#define PT_PROBE(k, tid) do { } while (0)
+#endif
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
 {
@@ -108,12 +134,13 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 // conversion so a frame that is cold in L2/HBM costs one memory round trip.
 // NROWS = rows staged into s_in rows 0..NROWS-1 (109 for a whole footprint, 45 for the next batch of a marching strip).
 // f32 frames: lane = column (+32q), coalesced 4-byte loads.
-template <int NROWS>
+template <int NROWS, int FCOLS = FC, int PITCH = PIN>
 __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H, int W, int fy0, int fx0,
                                            float fill, float *s_in, int warp, int lane)
 {
     constexpr int RPW = (NROWS + NWARPS - 1) / NWARPS;   // 14 rows per warp for a footprint (last ones masked)
-    float px[RPW][4];
+    constexpr int NQ = (FCOLS + 31) / 32;
+    float px[RPW][NQ];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
@@ -121,19 +148,19 @@ __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H,
         const bool yok = (f < NROWS) && (Y >= 0) && (Y < H);
         const float *rowp = frame + (size_t)(yok ? Y : 0) * pitch;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const int c = lane + 32 * q;
             const int X = fx0 + c;
-            px[r][q] = (yok && c < FC && X >= 0 && X < W) ? __ldg(rowp + X) : fill;
+            px[r][q] = (yok && c < FCOLS && X >= 0 && X < W) ? __ldg(rowp + X) : fill;
         }
     }
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = warp + r * NWARPS;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const int c = lane + 32 * q;
-            if (f < NROWS && c < FC) s_in[f * PIN + c] = px[r][q] - fill;
+            if (f < NROWS && c < FCOLS) s_in[f * PITCH + c] = px[r][q] - fill;
         }
     }
 }
@@ -145,7 +172,7 @@ __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H,
 // exact.  Each lane rotates its word by lane/8 bytes so the four stores of a warp hit 32
 // distinct banks.  Requires frame base, pitch and strides to be multiples of 4 bytes and
 // pitch ≥ round_up(W, 4) (checked by window45_supported).
-template <int NROWS, bool kInterior>
+template <int NROWS, bool kInterior, int FCOLS = FC, int PITCH = PIN>
 __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
                                               float fill, float *s_in, int warp, int lane)
 {
@@ -159,14 +186,14 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
 #pragma unroll
         for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < W) keep |= 0xFFu << (8 * b);
     }
-    const bool wordok = keep != 0u && (4 * lane - phase < FC);
+    const bool wordok = keep != 0u && (4 * lane - phase < FCOLS);
     const int rot = lane >> 3;
     int col[4];
     bool cok[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         col[k] = 4 * lane - phase + ((k + rot) & 3);
-        cok[k] = col[k] >= 0 && col[k] < FC;
+        cok[k] = col[k] >= 0 && col[k] < FCOLS;
     }
     unsigned int wd[RPW];
     // one running row pointer (bumped by NWARPS rows per load): two integer instructions per load instead of a
@@ -191,7 +218,7 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
         if (f < NROWS) {
             unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
             w = __funnelshift_r(w, w, 8 * rot);            // byte k of w = pixel (k + rot) & 3 of the word
-            float *dst = s_in + f * PIN;
+            float *dst = s_in + f * PITCH;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float val = __uint_as_float(__byte_perm(w, magic, c_prmt_sel[k])) - cst;
@@ -201,14 +228,15 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
     }
 }
 
-template <int NROWS>
+template <int NROWS, int FCOLS = FC, int PITCH = PIN>
 __device__ __forceinline__ void stage_rows(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
                                            float fill, float *s_in, int warp, int lane)
 {
     // interior: every aligned word the rows touch lies inside the frame → no byte masks, no row checks
-    const bool interior = (fy0 >= 0) && (fy0 + NROWS <= H) && ((fx0 & ~3) >= 0) && ((fx0 & ~3) + 4 * 28 <= W);
-    if (interior) stage_rows_u8<NROWS, true>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
-    else stage_rows_u8<NROWS, false>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    constexpr int NWORDS = (FCOLS + 3 + 3) / 4;               // aligned words covering FCOLS columns at any phase (28 for 109)
+    const bool interior = (fy0 >= 0) && (fy0 + NROWS <= H) && ((fx0 & ~3) >= 0) && ((fx0 & ~3) + 4 * NWORDS <= W);
+    if (interior) stage_rows_u8<NROWS, true, FCOLS, PITCH>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    else stage_rows_u8<NROWS, false, FCOLS, PITCH>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
 }
 
 template <typename PixT>
@@ -353,15 +381,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
 
     for (int t = 0; t < a.T; ++t) {
         const unsigned int it = (unsigned int)t;
-        long long *dbg = a.dbg ? a.dbg + ((size_t)v * a.T + t) * 6 : nullptr;
-        if (dbg && tid == 0) {
-            unsigned int smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            unsigned long long gt;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-            dbg[0] = ((long long)gt << 8) | (long long)(smid & 0xFF);   // wall-clock ns and SM id at window start
-            dbg[1] = clock64();
-        }
+        PT_PROBE_BEGIN(a, v, t, tid)
         const PixT *frame = a.frame_ptrs
             ? reinterpret_cast<const PixT *>(a.frame_ptrs[(size_t)t * a.n + v])
             : reinterpret_cast<const PixT *>(a.frames) + (size_t)t * a.step_stride + (size_t)v * a.frame_stride;
@@ -395,7 +415,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             while (atomicCAS(&s_rowlock, 0, 1) != 0) __nanosleep(40);
         }
         bar_half(half);
-        if (dbg && tid == 0) dbg[2] = clock64();
+        PT_PROBE(2, tid);
         if (tokens) {                                          // wait for the row-pass token
             if (half == 0) { if (round >= 1 && round - 1 < NB) asm volatile("bar.sync 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
             else           { if (round < NA) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
@@ -409,7 +429,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             else           { if (round + 1 < NA) asm volatile("bar.arrive 4, %0;" ::"n"(CTA_THREADS) : "memory"); }
         }
         ++round;
-        if (dbg && tid == 0) dbg[3] = clock64();
+        PT_PROBE(3, tid);
 
         unsigned long long key = col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr);
 #pragma unroll
@@ -419,7 +439,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         }
         if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
         bar_half(half);
-        if (dbg && tid == 0) dbg[4] = clock64();
+        PT_PROBE(4, tid);
         {
             // every thread folds the 8 warp keys itself (broadcast loads): no serial section;
             // s_key is double-buffered by iteration parity
@@ -439,7 +459,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
                     a.out_pos[v] = p; a.out_resp[v] = resp;
                     if (a.next_guess) a.next_guess[v] = make_int2(ci, cj);
                 }
-                if (dbg) dbg[5] = clock64();
+                PT_PROBE(5, 0);
             }
             g = make_int2(ci, cj);
         }
@@ -541,15 +561,7 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
             }
             prev_v = v;
         }
-        long long *dbg = a.dbg ? a.dbg + ((size_t)v * a.T + t) * 6 : nullptr;
-        if (dbg && tid == 0) {
-            unsigned int smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            unsigned long long gt;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-            dbg[0] = ((long long)gt << 8) | (long long)(smid & 0xFF);
-            dbg[1] = clock64();
-        }
+        PT_PROBE_BEGIN(a, v, t, tid)
         const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)t * a.step_stride + (size_t)v * a.frame_stride;
         const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);
         const int fy0 = wy0 - HW, fx0 = wx0 - HW;
@@ -579,12 +591,12 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
             while (atomicCAS(&s_rowlock, 0, 1) != 0) __nanosleep(40);
         }
         bar_half(half);
-        if (dbg && tid == 0) dbg[2] = clock64();
+        PT_PROBE(2, tid);
 
         row_pass45(s_in, s_mid, tid, tp);
         bar_half(half);
         if (tid == 0) atomicExch(&s_rowlock, 0);
-        if (dbg && tid == 0) dbg[3] = clock64();
+        PT_PROBE(3, tid);
 
         unsigned long long key = col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr);
 #pragma unroll
@@ -594,7 +606,7 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
         }
         if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
         bar_half(half);
-        if (dbg && tid == 0) dbg[4] = clock64();
+        PT_PROBE(4, tid);
         {
             const unsigned long long *kk = s_key + (it & 1) * NWARPS;
             unsigned long long k = kk[0];
@@ -617,7 +629,7 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
                     const unsigned int f = (unsigned int)(t + 1);
                     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.xflag + v), "r"(f) : "memory");
                 }
-                if (dbg) dbg[5] = clock64();
+                PT_PROBE(5, 0);
             }
             g = make_int2(ci, cj);
         }
@@ -771,11 +783,512 @@ dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// dog_window45_cluster<PixT, C> — ONE window spread over a thread-block cluster of C CTAs (C = 2, 4, 8), for
+// batches with fewer windows than SMs (a single video above all: the frame loop ij[t] = trckr(ij[t-1]),
+// src/PawsomeTracker.jl:167, is a serial chain, so a lone window is pure latency).
+//
+// The 45 output columns are cut into C slices.  Both passes of a slice are independent of the other slices:
+// the column pass of output column x only needs the row-pass intermediate of column x, and that only needs the
+// pixels of columns x−32 … x+32.  So the CTAs of a cluster exchange NOTHING but their argmax candidates: each
+// warp stores its 64-bit key into the shared memory of every CTA of the cluster (DSMEM), one cluster barrier,
+// every CTA folds the 8·C keys and knows the next guess.  The price is redundant staging (each CTA stages
+// 109 × (slice + 64) pixels).
+//
+// Staging (u8 frames, 16-byte aligned rows): the next window centre lies inside the current window, so the
+// region any next footprint can touch — 153 rows × (slice + 64 + 44) bytes — is known one step ahead.  It is
+// fetched with one cp.async.bulk (TMA) per row into a double-buffered u8 region in shared memory while the
+// current step computes; when the guess is known the footprint is converted u8 → f32 out of shared memory:
+// no global-memory latency on the serial chain.  A window that left the prefetched region (possible only when
+// the guess was outside the frame and got clamped) re-fetches its own region.  Other frames (f32, unaligned)
+// are staged straight from global memory with the L2 prefetch of dog_window45_argmax.
+//
+// Layouts: s_in [109][PINS] f32, PINS odd (lanes walk rows); s_midT [slice column][109] float2 — the column pass
+// walks rows of one column, items ordered row-group-fastest: consecutive items are 5·(item) float2 apart
+// (mod 16 bank pairs), i.e. conflict-free for any 16 consecutive lanes.
+// ---------------------------------------------------------------------------------------------------
+template <int C>
+struct SliceGeom {
+    static constexpr int SW = (WC + C - 1) / C;              // widest slice: 23 / 12 / 6 columns
+    static constexpr int RRS = 6;                            // row pass: outputs per thread
+    static constexpr int NGR = (SW + RRS - 1) / RRS;         // groups per row: 4 / 2 / 1
+    static constexpr int SWC = NGR * RRS;                    // computed columns (≥ SW; the surplus is masked)
+    static constexpr int SFC = SWC + 2 * HW;                 // staged footprint columns: 88 / 76 / 70
+    static constexpr int PINS = SFC | 1;                     // odd pitch
+    static constexpr int NW = (SFC + 3 + 3) / 4;             // aligned words per staged row at any phase
+    static constexpr int RC = (C == 8) ? 3 : 5;              // column pass: outputs per thread
+    static constexpr int NGC = WR / RC;                      // row groups: 9 / 15
+    static constexpr int RGN_ROWS = FR + 2 * (WR / 2);       // 153 rows any next footprint can touch
+    static constexpr int SPAN = ((4 * NW + 2 * (WC / 2) + 15 + 15) / 16) * 16;   // bytes per region row (16-byte aligned start)
+    static constexpr int RGN_BYTES = ((RGN_ROWS * SPAN + 127) / 128) * 128;   // 128-byte multiple: TMA tile destinations
+    static constexpr size_t IN_BYTES = ((size_t)FR * PINS * sizeof(float) + 15) & ~(size_t)15;
+    static constexpr size_t MID_BYTES = (size_t)SWC * FR * sizeof(float2);
+    static_assert(WR % RC == 0, "row groups must tile the window");
+    static_assert(NW <= 32, "one lane per staged word");
+    static_assert(SW * NGC <= 256 && RGN_ROWS <= 256, "one item / one region row per thread");
+    static size_t smem_bytes(bool bulk) { return (bulk ? 2 * (size_t)RGN_BYTES + 128 : 0) + IN_BYTES + MID_BYTES; }
+};
+constexpr int CL_THREADS = 256;
+
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned int mbar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int mbar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned int mbar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned int mbar, unsigned int parity)
+{
+    unsigned int ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// Wait for the phase with the given parity; a watchdog turns a lost copy into a launch error instead of a hang.
+__device__ __forceinline__ void mbar_wait(unsigned int mbar, unsigned int parity)
+{
+    if (mbar_try_wait(mbar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(mbar, parity)) {
+        if (clock64() - t0 > (1ll << 32)) __trap();          // ≈ 2 s at 2 GHz
+    }
+}
+// One row of a frame → shared memory through the TMA unit (cp.async.bulk → SASS UBLKCP); src, dst and size are
+// multiples of 16 bytes.
+__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void *src, unsigned int bytes, unsigned int mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(mbar) : "memory");
+}
+// The whole region of a step in ONE instruction: 2-D TMA tile copy (cp.async.bulk.tensor → SASS UTMALDG) out of the
+// tensor map that describes the resident frames as [rows][pitch] bytes; elements outside the tensor arrive as zeros
+// (and are masked by frame coordinates anyway).
+__device__ __forceinline__ void tma_tile_2d(unsigned int dst, const CUtensorMap *tmap, int x, int y, unsigned int mbar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned int cluster_rank()
+{
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u64(unsigned int local_addr, unsigned int rank, unsigned long long v)
+{
+    unsigned int remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
+}
+
+// u8 → f32 conversion of one footprint slice out of the prefetched u8 region in shared memory: the same word /
+// PRMT / 2^23 scheme as stage_rows_u8, LDS instead of LDG.  rgn row 0 ↔ frame row rgn_y0, rgn byte 0 ↔ frame
+// column rgn_xa (multiple of 16).  Bytes outside the frame were never copied: they are replaced by the fill byte.
+template <int C, bool kInterior>
+__device__ __forceinline__ void convert_slice_u8(const uint8_t *rgn, int rgn_y0, int rgn_xa, int H, int W, int fy0, int fxs,
+                                                 float fill, float *s_in, int warp, int lane)
+{
+    using G = SliceGeom<C>;
+    constexpr int RPW = (FR + NWARPS - 1) / NWARPS;
+    const int xw0 = fxs & ~3, phase = fxs - xw0;
+    const int X = xw0 + 4 * lane;
+    const unsigned int fillw = (unsigned int)fill * 0x01010101u;
+    unsigned int keep = 0xFFFFFFFFu;
+    if (!kInterior) {
+        keep = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < W) keep |= 0xFFu << (8 * b);
+    }
+    const bool wordok = keep != 0u && (4 * lane - phase < G::SFC);
+    const int rot = lane >> 3;
+    int col[4];
+    bool cok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        col[k] = 4 * lane - phase + ((k + rot) & 3);
+        cok[k] = col[k] >= 0 && col[k] < G::SFC;
+    }
+    unsigned int wd[RPW];
+    const uint8_t *src = rgn + (fy0 + warp - rgn_y0) * G::SPAN + (X - rgn_xa);
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int f = warp + r * NWARPS;
+        const int Y = fy0 + f;
+        const bool ok = wordok && (f < FR) && (kInterior || ((Y >= 0) && (Y < H)));
+        wd[r] = fillw;
+        if (ok) wd[r] = *reinterpret_cast<const unsigned int *>(src + r * (NWARPS * G::SPAN));
+    }
+    const float cst = 8388608.0f + fill;
+    const unsigned int magic = 0x4B000000u;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int f = warp + r * NWARPS;
+        if (f < FR) {
+            unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
+            w = __funnelshift_r(w, w, 8 * rot);
+            float *dst = s_in + f * G::PINS;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float val = __uint_as_float(__byte_perm(w, magic, c_prmt_sel[k])) - cst;
+                if (cok[k]) dst[col[k]] = val;
+            }
+        }
+    }
+}
+
+// Row pass of a slice: item = (footprint row f, group g of 6 output columns), lanes walk rows; same folded
+// arithmetic (and summation order) as row_pass45.  Output → s_midT[column][row].
+template <int C>
+__device__ __forceinline__ void row_pass_slice(const float *s_in, float2 *s_midT, int tid, const Taps45 &tp)
+{
+    using G = SliceGeom<C>;
+    constexpr int RRS = G::RRS;
+#pragma unroll 1
+    for (int item = tid; item < FR * G::NGR; item += CL_THREADS) {
+        const int g = item / FR, f = item - g * FR;
+        const float *row = s_in + f * G::PINS + g * RRS;
+        float x[RRS + 2 * HW];
+#pragma unroll
+        for (int i = 0; i < RRS + 2 * HW; ++i) x[i] = row[i];
+        float2 acc[RRS];
+#pragma unroll
+        for (int j = 0; j < RRS; ++j) acc[j] = fmul2(make_float2(x[j + HW], x[j + HW]), tp.rt[0]);
+#pragma unroll
+        for (int d = 1; d <= HW; ++d) {
+#pragma unroll
+            for (int j = 0; j < RRS; ++j) {
+                const float sm = x[j + HW - d] + x[j + HW + d];
+                acc[j] = ffma2(make_float2(sm, sm), tp.rt[d], acc[j]);
+            }
+        }
+        float2 *dst = s_midT + (g * RRS) * FR + f;
+#pragma unroll
+        for (int j = 0; j < RRS; ++j) dst[j * FR] = acc[j];
+    }
+}
+
+// Column pass of a slice + per-thread argmax: item = (slice column x, group h of RC output rows), h fastest.
+// Same per-output operation order as col_pass45 (packed pairs of vertically adjacent outputs, narrow and wide
+// parts accumulated separately, added at the end).  `width` columns of the slice are real; the slice's column 0
+// is column gx0 of a wr_tot × wc_tot output rectangle whose row 0 is this tile's row gy0.
+template <int C>
+__device__ __forceinline__ unsigned long long col_pass_slice(const float2 *s_midT, int tid, const Taps45 &tp, int width,
+                                                             int gy0, int gx0, int wr_tot, int wc_tot)
+{
+    using G = SliceGeom<C>;
+    constexpr int RC = G::RC, NP = RC / 2;
+    if (tid >= G::SW * G::NGC) return 0ull;
+    const int x = tid / G::NGC, h = tid - x * G::NGC;
+    const float2 *col = s_midT + x * FR + h * RC;
+    float2 accP[NP], accM[NP];
+    float acc_lp = 0.f, acc_lm = 0.f;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int i = 0; i < RC + 2 * HW; ++i) {
+        const float2 m = col[i];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int q = i - 2 * p;
+            if (q >= 0 && q <= L) accP[p] = ffma2(make_float2(m.x, m.x), tp.cpp[q], accP[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int q = i - 2 * p;
+            if (q >= 0 && q <= L) accM[p] = ffma2(make_float2(m.y, m.y), tp.cmq[q], accM[p]);
+        }
+        const int ql = i - (RC - 1);
+        if (ql >= 0 && ql < L) {
+            acc_lp = fmaf(m.x, tp.cpp[ql].x, acc_lp);
+            acc_lm = fmaf(m.y, tp.cmq[ql].x, acc_lm);
+        }
+    }
+    float acc[RC];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { acc[2 * p] = accP[p].x + accM[p].x; acc[2 * p + 1] = accP[p].y + accM[p].y; }
+    acc[RC - 1] = acc_lp + acc_lm;
+    const int gx = gx0 + x, gyb = gy0 + h * RC;
+    if (x >= width || gx >= wc_tot || gyb >= wr_tot) return 0ull;
+    float bv = acc[0] + 0.0f;
+    int bj = 0;
+#pragma unroll
+    for (int j = 1; j < RC; ++j) {
+        const float val = acc[j] + 0.0f;
+        if (gyb + j < wr_tot && val > bv) { bv = val; bj = j; }
+    }
+    return pack_key(bv, (unsigned int)(gx * wr_tot + gyb + bj));
+}
+
+template <typename PixT, int C>
+__global__ void __launch_bounds__(CL_THREADS, 2)
+dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ Taps45 tp, const int use_bulk,
+                     const __grid_constant__ CUtensorMap tmap)
+{
+    using G = SliceGeom<C>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    __shared__ __align__(8) unsigned long long s_xk[2][NWARPS * C];      // candidates of every warp of every CTA of the cluster
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_rank();
+    const int v = (int)blockIdx.x / C;
+    const int xs = (WC * rank) / C, width = (WC * (rank + 1)) / C - xs;  // this CTA's output columns [xs, xs + width)
+    constexpr bool kU8 = sizeof(PixT) == 1;
+    const bool bulk = kU8 && use_bulk != 0;
+    unsigned char *rgn = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);      // 128-byte aligned (TMA tile destination)
+    float *s_in = reinterpret_cast<float *>(smem_raw + (bulk ? 2 * G::RGN_BYTES + 128 : 0));
+    float2 *s_midT = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(s_in) + G::IN_BYTES);
+    const unsigned int mbar0 = smem_u32(&s_mbar[0]);
+    const unsigned int rgn0 = smem_u32(rgn);
+
+    if (tid == 0) {
+        mbar_init(mbar0, 1u);
+        mbar_init(mbar0 + 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_arrive();            // no CTA touches a peer's shared memory before every CTA of the cluster runs
+    cluster_wait();
+
+    const float fill = a.fill[v];
+    int2 g = a.guess[v];
+    const PixT *frame0 = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
+    int rgn_y0[2] = {0, 0}, rgn_xa[2] = {0, 0};
+    unsigned int ph[2] = {0u, 0u};
+
+    // request the region around footprint origin (cfy0, cfxs) of step `ts` (frame `frame`) into buffer `buf`:
+    // use_bulk 2 → one TMA tile copy, use_bulk 1 → one bulk copy per row
+    auto issue_region = [&](int buf, const PixT *frame, int ts, int cfy0, int cfxs) {
+        const int y0 = cfy0 - WR / 2, xa = (cfxs - WC / 2) & ~15;
+        rgn_y0[buf] = y0; rgn_xa[buf] = xa;
+        if (use_bulk == 2) {
+            if (tid == 0) {
+                const unsigned int mb = mbar0 + 8u * (unsigned int)buf;
+                mbar_arrive_expect_tx(mb, (unsigned int)(G::RGN_ROWS * G::SPAN));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tma_tile_2d(rgn0 + (unsigned int)(buf * G::RGN_BYTES), &tmap, xa, ts * a.tm_rows_step + v * a.tm_rows_frame + y0, mb);
+            }
+            return;
+        }
+        const int lo = max(xa, 0), hi = min(xa + G::SPAN, a.pitch);
+        const int nb = hi - lo;
+        const int ylo = max(y0, 0), yhi = min(y0 + G::RGN_ROWS, a.H);
+        const unsigned int mb = mbar0 + 8u * (unsigned int)buf;
+        if (tid == 0) {
+            if (nb > 0 && yhi > ylo) mbar_arrive_expect_tx(mb, (unsigned int)(nb * (yhi - ylo)));
+            else mbar_arrive(mb);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int Y = y0 + tid;
+        if (tid < G::RGN_ROWS && nb > 0 && Y >= 0 && Y < a.H)
+            bulk_g2s(rgn0 + (unsigned int)(buf * G::RGN_BYTES + tid * G::SPAN + (lo - xa)),
+                     reinterpret_cast<const unsigned char *>(frame) + (size_t)Y * a.pitch + lo, (unsigned int)nb, mb);
+    };
+
+    if (bulk) issue_region(0, frame0, 0, g.x - 1 - (WR / 2) - HW, g.y - 1 - (WC / 2) - HW + xs);
+
+    for (int t = 0; t < a.T; ++t) {
+        const int par = t & 1;
+        PT_PROBE_BEGIN(a, v, t, tid + rank)
+        const PixT *frame = frame0 + (size_t)t * a.step_stride;
+        const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);
+        const int fy0 = wy0 - HW, fxs = wx0 - HW + xs;                       // footprint origin of this slice
+        if (bulk) {
+            const int xw0 = fxs & ~3;
+            const bool covered = fy0 >= rgn_y0[par] && fy0 + FR <= rgn_y0[par] + G::RGN_ROWS &&
+                                 xw0 >= rgn_xa[par] && xw0 + 4 * G::NW <= rgn_xa[par] + G::SPAN;
+            mbar_wait(mbar0 + 8u * par, ph[par]); ph[par] ^= 1u;
+            if (!covered) {                                                  // (uniform) the window left the prefetched region
+                __syncthreads();                                             // every thread has seen the completed phase
+                issue_region(par, frame, t, fy0, fxs);
+                mbar_wait(mbar0 + 8u * par, ph[par]); ph[par] ^= 1u;
+            }
+            const bool interior = fy0 >= 0 && fy0 + FR <= a.H && xw0 >= 0 && xw0 + 4 * G::NW <= a.W;
+            const uint8_t *rb = rgn + par * G::RGN_BYTES;
+            if (interior) convert_slice_u8<C, true>(rb, rgn_y0[par], rgn_xa[par], a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
+            else convert_slice_u8<C, false>(rb, rgn_y0[par], rgn_xa[par], a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
+            // everything the next step can touch → the other buffer (last read by the previous step's conversion)
+            if (t + 1 < a.T) issue_region(par ^ 1, frame + a.step_stride, t + 1, fy0, fxs);
+        } else {
+            stage_rows<FR, G::SFC, G::PINS>(frame, a.pitch, a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
+            if (t + 1 < a.T) {                                               // warm L2 with the next step's region
+                const PixT *nframe = frame + a.step_stride;
+                constexpr int NLMAX = (int)(((G::SFC + WC) * sizeof(PixT) + 127) / 128) + 1;
+                const int pxb = (fxs - WC / 2) * (int)sizeof(PixT);
+                const int line0 = pxb >> 7;
+                const int nl = ((pxb + (G::SFC + WC - 1) * (int)sizeof(PixT) - 1) >> 7) - line0 + 1;
+                const int rowbytes = a.W * (int)sizeof(PixT);
+                const int Y = fy0 - WR / 2 + tid;
+                if (tid < G::RGN_ROWS && Y >= 0 && Y < a.H) {
+                    const char *ptr = reinterpret_cast<const char *>(nframe + (size_t)Y * a.pitch) + (line0 << 7);
+#pragma unroll
+                    for (int ln = 0; ln < NLMAX; ++ln) {
+                        const int off = (line0 + ln) << 7;
+                        if (ln < nl && off >= 0 && off < rowbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (ln << 7)));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        PT_PROBE(2, tid + rank);
+
+        row_pass_slice<C>(s_in, s_midT, tid, tp);
+        __syncthreads();
+        PT_PROBE(3, tid + rank);
+
+        unsigned long long key = col_pass_slice<C>(s_midT, tid, tp, width, 0, xs, WR, WC);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+            key = o > key ? o : key;
+        }
+        // every warp hands its candidate to every CTA of the cluster (its own included), slots double-buffered by
+        // step parity: a CTA can only overwrite slot `par` two steps later, i.e. after the next cluster barrier,
+        // which every CTA reaches only after it has read this step's slots
+        if (lane < C) st_cluster_u64(smem_u32(&s_xk[par][rank * NWARPS + warp]), (unsigned int)lane, key);
+        cluster_arrive();
+        cluster_wait();
+        PT_PROBE(4, tid + rank);
+        {
+            unsigned long long k = s_xk[par][lane % (NWARPS * C)];
+            if (NWARPS * C > 32) { const unsigned long long k2 = s_xk[par][32 + lane]; k = k2 > k ? k2 : k; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, k, off);
+                k = o > k ? o : k;
+            }
+            const unsigned int idx = key_index(k);
+            const int xx = (int)(idx / WR), yy = (int)(idx - xx * WR);
+            const int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;                   // absolute index (:60)
+            const int ci = min(max(raw_i, 1), a.H), cj = min(max(raw_j, 1), a.W);   // clamp (:61)
+            if (tid == 0 && rank == 0) {
+                const float resp = key_value(k);
+                const int4 p = make_int4(ci, cj, raw_i, raw_j);
+                if (a.traj_pos) { a.traj_pos[(size_t)t * a.n + v] = p; a.traj_resp[(size_t)t * a.n + v] = resp; }
+                if (t == a.T - 1) {
+                    a.out_pos[v] = p; a.out_resp[v] = resp;
+                    if (a.next_guess) a.next_guess[v] = make_int2(ci, cj);
+                }
+                PT_PROBE(5, 0);
+            }
+            g = make_int2(ci, cj);
+        }
+    }
+    // (the last cluster barrier above already ordered every remote store before any CTA can exit)
+}
+
+// How many CTAs share one window for this launch (1 = the per-SM kernels above).
+static int cluster_size_for(const WinArgs &a, const Cfg &cfg, int n)
+{
+    if (cfg.cluster == 1 || a.frame_ptrs) return 1;
+    if (cfg.cluster == 2 || cfg.cluster == 4 || cfg.cluster == 8) return cfg.cluster;
+    const int sms = cfg.sms;
+    if (8 * n <= sms) return 8;
+    if (4 * n <= sms) return 4;
+    if (2 * n <= sms) return 2;
+    return 1;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda: the library must load
+// on a machine without a driver).  nullptr = unavailable → the row-bulk mode is used instead.
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder()
+{
+    static tmap_encode_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (tmap_encode_fn)sym;
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+template <typename PixT, int C>
+static cudaError_t launch_cluster_t(Args45 k, const Taps45 &tp, int use_bulk, cudaStream_t s)
+{
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (use_bulk == 2) {
+        // the resident frames as one 2-D u8 tensor [rows][pitch]: row of (step t, video v, frame row y) =
+        // t·rows_step + v·rows_frame + y.  Needs strides that are whole rows; else fall back to row copies.
+        tmap_encode_fn enc = tmap_encoder();
+        const bool regular = enc && k.pitch > 0 && k.frame_stride % (size_t)k.pitch == 0 && k.step_stride % (size_t)k.pitch == 0;
+        bool ok = false;
+        if (regular) {
+            k.tm_rows_frame = (int)(k.frame_stride / (size_t)k.pitch);
+            k.tm_rows_step = (int)(k.step_stride / (size_t)k.pitch);
+            const cuuint64_t rows = (cuuint64_t)(k.T - 1) * (cuuint64_t)k.tm_rows_step + (cuuint64_t)(k.n - 1) * (cuuint64_t)k.tm_rows_frame + (cuuint64_t)k.H;
+            const cuuint64_t dims[2] = {(cuuint64_t)k.pitch, rows};
+            const cuuint64_t strides[1] = {(cuuint64_t)k.pitch};
+            const cuuint32_t box[2] = {(cuuint32_t)SliceGeom<C>::SPAN, (cuuint32_t)SliceGeom<C>::RGN_ROWS};
+            const cuuint32_t estr[2] = {1u, 1u};
+            ok = rows < (1ull << 31) &&
+                 enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2u, const_cast<void *>(k.frames), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        if (!ok) use_bulk = 1;
+    }
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3((unsigned)(k.n * C));
+    lc.blockDim = dim3(CL_THREADS);
+    lc.dynamicSmemBytes = SliceGeom<C>::smem_bytes(use_bulk != 0);
+    lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, dog_window45_cluster<PixT, C>, k, tp, use_bulk, tmap);
+}
+
+static cudaError_t launch_cluster(const Args45 &k, const Taps45 &tp, const Cfg &cfg, int C, int pixel, cudaStream_t s)
+{
+    // the TMA path needs 16-byte aligned rows
+    const bool aligned16 = pixel == 0 && ((reinterpret_cast<uintptr_t>(k.frames) | (uintptr_t)k.pitch | (uintptr_t)k.frame_stride |
+                                           (uintptr_t)k.step_stride) & 15u) == 0;
+    const int use_bulk = (cfg.bulk && aligned16) ? cfg.bulk : 0;        // 1: one bulk copy per region row, 2: one TMA tile copy
+    if (pixel == 0) {
+        if (C == 2) return launch_cluster_t<uint8_t, 2>(k, tp, use_bulk, s);
+        if (C == 4) return launch_cluster_t<uint8_t, 4>(k, tp, use_bulk, s);
+        return launch_cluster_t<uint8_t, 8>(k, tp, use_bulk, s);
+    }
+    if (C == 2) return launch_cluster_t<float, 2>(k, tp, 0, s);
+    if (C == 4) return launch_cluster_t<float, 4>(k, tp, 0, s);
+    return launch_cluster_t<float, 8>(k, tp, 0, s);
+}
+
+#define PT_CLUSTER_OPTINS                                                            \
+    PT_OPTIN((dog_window45_cluster<uint8_t, 2>), SliceGeom<2>::smem_bytes(true))     \
+    PT_OPTIN((dog_window45_cluster<uint8_t, 4>), SliceGeom<4>::smem_bytes(true))     \
+    PT_OPTIN((dog_window45_cluster<uint8_t, 8>), SliceGeom<8>::smem_bytes(true))     \
+    PT_OPTIN((dog_window45_cluster<float, 2>), SliceGeom<2>::smem_bytes(false))      \
+    PT_OPTIN((dog_window45_cluster<float, 4>), SliceGeom<4>::smem_bytes(false))      \
+    PT_OPTIN((dog_window45_cluster<float, 8>), SliceGeom<8>::smem_bytes(false))
+
+// ===================================================================================================
+// host side
+// ===================================================================================================
 const char *rect45_name() { return "dog_rect45_march"; }
 
-bool rect45_supported(const WinArgs &a, int pixel)
+bool rect45_supported(const WinArgs &a, const Cfg &cfg, int pixel)
 {
-    if (a.L != L || getenv("PT_DISABLE_RECT45")) return false;
+    if (a.L != L || !cfg.rect45) return false;
     if ((long long)a.wr * a.wc < 24 * 24) return false;     // tiny windows: the generic strip kernel wastes less
     if (pixel == 0) {
         const bool aligned = ((reinterpret_cast<uintptr_t>(a.frames) | (uintptr_t)a.pitch | (uintptr_t)a.frame_stride) & 3u) == 0;
@@ -786,9 +1299,10 @@ bool rect45_supported(const WinArgs &a, int pixel)
 
 const char *window45_name() { return "dog_window45_argmax"; }
 
+#ifdef PT_PROBES
 static long long *g_dbg = nullptr;
 void window45_set_debug(long long *dev_buf) { g_dbg = dev_buf; }
-long long *window45_debug_ptr() { return g_dbg; }
+#endif
 
 bool window45_supported(const WinArgs &a, int pixel)
 {
@@ -803,7 +1317,7 @@ bool window45_supported(const WinArgs &a, int pixel)
     return true;
 }
 
-// The specialised kernel takes its taps as kernel parameters (constant bank):
+// The specialised kernels take their taps as kernel parameters (constant bank):
 // fold the symmetric row factors (index d = |k − 32|) and pair the column taps.
 static void fold_taps(const WinArgs &a, Taps45 &tp)
 {
@@ -816,34 +1330,47 @@ static void fold_taps(const WinArgs &a, Taps45 &tp)
     }
 }
 
-static int sm_count()
+// Once per (process, device), with the device current (pt_batch_create holds the lock): dynamic shared memory
+// opt-in of every kernel of this file.
+cudaError_t window45_init_device()
 {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, vsm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&vsm, cudaDevAttrMultiProcessorCount, dev);
-        sms = vsm > 0 ? vsm : 148;
-    }
-    return sms;
+    const int smem = (int)(2 * HALF_SMEM);
+    cudaError_t e;
+#define PT_OPTIN(k, bytes)                                                                      \
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));       \
+    if (e != cudaSuccess) return e;
+    PT_OPTIN(dog_window45_argmax<uint8_t>, smem)
+    PT_OPTIN(dog_window45_argmax<float>, smem)
+    PT_OPTIN(dog_window45_rot<uint8_t>, smem)
+    PT_OPTIN(dog_window45_rot<float>, smem)
+    PT_OPTIN(dog_rect45_march<uint8_t>, smem)
+    PT_OPTIN(dog_rect45_march<float>, smem)
+    PT_CLUSTER_OPTINS
+#undef PT_OPTIN
+    return cudaSuccess;
 }
 
 // S < n < 2S with not too many empty slots, frames in HBM, more than one step: rotate the empty slots
 // (dog_window45_rot)
-bool window45_uses_rot(const WinArgs &a, int n)
+static bool uses_rot(const WinArgs &a, const Cfg &cfg, int n)
 {
-    const char *rot_env = getenv("PT_W45_ROT");
-    const int rot_on = rot_env ? atoi(rot_env) : 1;
-    const int sms = sm_count();
+    const int sms = cfg.sms;
     // every step nh = 2S − n windows hop (≈ 2.5 K cycles of hand-off latency each): measured worthwhile up to
-    // nh ≈ 0.7·n (n ≥ 1.18·S: 9.3 vs 9.9 µs per step at n = 180, break-even at n = 160); PT_W45_ROT=2 forces it
-    const bool few_holes = rot_on == 2 || 10 * (2 * sms - n) <= 7 * n;
-    return rot_on && a.xflag && a.xpos && !a.frame_ptrs && a.T > 1 && n > sms && n < 2 * sms && few_holes;
+    // nh ≈ 0.7·n (n ≥ 1.18·S: 9.3 vs 9.9 µs per step at n = 180, break-even at n = 160); rot = 2 forces it
+    const bool few_holes = cfg.rot == 2 || 10 * (2 * sms - n) <= 7 * n;
+    return cfg.rot && a.xflag && a.xpos && !a.frame_ptrs && a.T > 1 && n > sms && n < 2 * sms && few_holes;
 }
 
-const char *window45_rot_name() { return "dog_window45_rot"; }
+const char *window45_kernel_for(const WinArgs &a, const Cfg &cfg, int n)
+{
+    const int C = cluster_size_for(a, cfg, n);
+    if (C == 2) return "dog_window45_cluster<2>";
+    if (C == 4) return "dog_window45_cluster<4>";
+    if (C == 8) return "dog_window45_cluster<8>";
+    return uses_rot(a, cfg, n) ? "dog_window45_rot" : "dog_window45_argmax";
+}
 
-cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
+cudaError_t launch_window45(const WinArgs &a, const Cfg &cfg, int n, int pixel, cudaStream_t s)
 {
     if (!a.h_taps) return cudaErrorInvalidValue;
     Taps45 tp;
@@ -857,38 +1384,35 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
     k.n = n;
     k.out_pos = a.out_pos; k.out_resp = a.out_resp; k.next_guess = a.next_guess;
     k.traj_pos = a.traj_pos; k.traj_resp = a.traj_resp;
+#ifdef PT_PROBES
     k.dbg = g_dbg;
-    {
-        static int skew = -1;
-        if (skew < 0) { const char *e2 = getenv("PT_W45_SKEW"); skew = e2 ? atoi(e2) : 1; }
-        k.skew = skew;
+#endif
+    k.skew = cfg.skew;
+    k.tm_rows_step = 0; k.tm_rows_frame = 0;
+    k.xflag = a.xflag; k.xpos = a.xpos;
+    const int C = cluster_size_for(a, cfg, n);
+    if (C > 1) {
+        e = launch_cluster(k, tp, cfg, C, pixel, s);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();                  // cluster launch refused (e.g. MIG slice without clusters): fall through
     }
-    const int sms = sm_count();
+    const int sms = cfg.sms;
     // one CTA per SM, two windows per CTA; with n ≤ #SMs every window gets its own SM
     const int grid = std::min(sms, n);
     const size_t smem = 2 * HALF_SMEM;
-    k.xflag = a.xflag; k.xpos = a.xpos;
-    if (window45_uses_rot(a, n)) {
+    if (uses_rot(a, cfg, n)) {
         void *params[2] = {(void *)&k, (void *)&tp};
-        if (pixel == 0) {
-            { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_rot<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
+        if (pixel == 0)
             e = cudaLaunchCooperativeKernel((const void *)dog_window45_rot<uint8_t>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
-        } else {
-            { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_rot<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
+        else
             e = cudaLaunchCooperativeKernel((const void *)dog_window45_rot<float>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
-        }
         if (e == cudaSuccess) return e;
         // the CTAs cannot all be co-resident right now (device shared with other work): the windows cannot hop
         // safely — run the static split instead
         cudaGetLastError();
     }
-    if (pixel == 0) {
-        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_argmax<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-        dog_window45_argmax<uint8_t><<<grid, CTA_THREADS, smem, s>>>(k, tp);
-    } else {
-        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_window45_argmax<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-        dog_window45_argmax<float><<<grid, CTA_THREADS, smem, s>>>(k, tp);
-    }
+    if (pixel == 0) dog_window45_argmax<uint8_t><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+    else dog_window45_argmax<float><<<grid, CTA_THREADS, smem, s>>>(k, tp);
     return cudaGetLastError();
 }
 
@@ -898,9 +1422,9 @@ cudaError_t launch_window45(const WinArgs &a, int n, int pixel, cudaStream_t s)
 // a pair.  Measured behaviour of the ticket scheduler: the halves of an SM finish together and fetch together, so
 // with few rounds the makespan is ceil(items / 2·SMs) whole items; with many rounds it tends to
 // total work / (2·SMs) plus half an item of tail.
-int rect45_pick_chunks(int n, int ntx, int nty, int sms)
+int rect45_pick_chunks(int n, int ntx, int nty, int sms, int forced)
 {
-    if (const char *e = getenv("PT_R45_CHUNKS")) { const int c = atoi(e); if (c >= 1) return std::min(c, nty); }
+    if (forced >= 1) return std::min(forced, nty);
     int best_c = nty;
     double best_cost = 1e300;
     for (int c = 1; c <= nty; ++c) {
@@ -918,35 +1442,23 @@ int rect45_pick_chunks(int n, int ntx, int nty, int sms)
     return best_c;
 }
 
-cudaError_t launch_rect45(const WinArgs &a, int n, int pixel, cudaStream_t s)
+cudaError_t launch_rect45(const WinArgs &a, const Cfg &cfg, int n, int pixel, cudaStream_t s)
 {
     if (!a.h_taps) return cudaErrorInvalidValue;
     Taps45 tp;
     fold_taps(a, tp);
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, vsm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&vsm, cudaDevAttrMultiProcessorCount, dev);
-        sms = vsm > 0 ? vsm : 148;
-    }
+    const int sms = cfg.sms;
     March45 m;
     m.n = n;
     m.nty = (a.wr + WR - 1) / WR;
     m.ntx = (a.wc + WC - 1) / WC;
-    m.nchunks = rect45_pick_chunks(n, m.ntx, m.nty, sms);
+    m.nchunks = rect45_pick_chunks(n, m.ntx, m.nty, sms, cfg.r45_chunks);
     const long long items = (long long)n * m.ntx * m.nchunks;
     // one CTA per SM; with fewer items than SMs every item gets an SM to itself (second halves stay idle)
     const int grid = (int)std::max<long long>(1, std::min<long long>(sms, items));
     const size_t smem = 2 * HALF_SMEM;
-    cudaError_t e;
-    if (pixel == 0) {
-        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect45_march<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-        dog_rect45_march<uint8_t><<<grid, CTA_THREADS, smem, s>>>(a, tp, m);
-    } else {
-        { static size_t set_for = 0; if (set_for < smem) { e = cudaFuncSetAttribute(dog_rect45_march<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set_for = smem; } }
-        dog_rect45_march<float><<<grid, CTA_THREADS, smem, s>>>(a, tp, m);
-    }
+    if (pixel == 0) dog_rect45_march<uint8_t><<<grid, CTA_THREADS, smem, s>>>(a, tp, m);
+    else dog_rect45_march<float><<<grid, CTA_THREADS, smem, s>>>(a, tp, m);
     return cudaGetLastError();
 }
 

@@ -111,6 +111,11 @@ class TrackerBatch:
         self.window_size = (int(window_size[0]), int(window_size[1]))
         self.radii = (self.window_size[0] // 2, self.window_size[1] // 2)
 
+    def set_option(self, name: str, value: int):
+        """Per-handle tuning / debugging knob (pt_batch_set_option): "window45", "rect45", "rot", "skew",
+        "r45_chunks", "generic_target", "mode_slow", "zero_copy", "host_lanes", "cluster", "bulk"."""
+        check(lib.pt_batch_set_option(self._h, name.encode(), int(value)))
+
     def set_frames(self, frames):
         """frames: sequence of n HxW arrays (host)."""
         if len(frames) != self.n:
@@ -317,6 +322,9 @@ class Tracker:
         """`imresize!` of the current host frame (uploaded whole) on the device — diagnostics only."""
         self._batch.set_frames([self.img])
         return self._batch.downscale(out_h, out_w)[0]
+
+    def set_option(self, name: str, value: int):
+        self._batch.set_option(name, value)
 
     def close(self):
         self._batch.close()

@@ -21,6 +21,13 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def synth():
+    """The reference's synthetic-video test recipe (tools/synth.py): test infrastructure, not part of the package."""
+    from tools import synth as m
+    return m
+
+
+@pytest.fixture(scope="session")
 def pkg():
     """The product package. Importing it requires the built libpawsome_cuda.so."""
     so = os.path.join(ROOT, "pawsometracker.jl_b200", "libpawsome_cuda.so")

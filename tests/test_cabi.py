@@ -36,6 +36,30 @@ def test_library_exports_every_declared_symbol(pkg):
     assert set(pkg._lib.SIGNATURES) == set(declared_symbols())
 
 
+def test_product_library_exports_no_measurement_or_debug_entry_points(pkg):
+    """north_star: "hand-written kernels and nothing else on this path" — the FP32-peak measurement, the issue probe,
+    the L2 flush and the phase-timestamp hook live in libpawsome_bench.so / the -DPT_PROBES build, not in the product."""
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (pt[a-z]*_[a-z0-9_]+)", out))
+    bad = [s for s in exported if re.match(r"pt_(measure|probe|debug|flush)", s) or s.startswith("ptb_")]
+    assert not bad, bad
+    bench = os.path.join(os.path.dirname(pkg.LIB_PATH), "libpawsome_bench.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", bench], capture_output=True, text=True, check=True).stdout
+    bexp = set(re.findall(r" T (ptb_[a-z0-9_]+)", out))
+    hdr = open(os.path.join(ROOT, "include", "pawsome_bench.h")).read()
+    assert bexp == set(re.findall(r"^PTB_API\s+[^;(]*?\b(ptb_[a-z0-9_]+)\s*\(", hdr, flags=re.M)) and len(bexp) == 3
+    # the kernels of the product library carry no probe code: no clock / globaltimer reads in its SASS
+    sass = subprocess.run(["cuobjdump", "-sass", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    if sass:
+        assert "SR_GLOBALTIMER" not in sass
+
+
+def test_options_are_per_handle_and_validated(pkg):
+    assert pkg.lib.pt_batch_set_option(None, b"rot", 0) == -1
+    # names and ranges are checked without a device through the error text only when a handle exists; here: NULL handle
+    assert "NULL" in pkg._lib.last_error()
+
+
 def test_header_is_plain_c():
     """The boundary must compile as C (no torch / C++ types in the signatures)."""
     code = '#include "pawsome.h"\nint main(void){return pt_version()==0;}\n'

@@ -43,38 +43,38 @@ def test_resampling_indices(pkg):
     assert n == 10
 
 
-def test_partition_overlaps_by_one(pkg):
-    parts = pkg.my_partition(241, 3)                      # test/test-basic-test.jl:43-49
+def test_partition_overlaps_by_one(pkg, synth):
+    parts = synth.my_partition(241, 3)                      # test/test-basic-test.jl:43-49
     assert parts[0][0] == 0 and parts[-1][1] == 240
     for (a0, a1), (b0, b1) in zip(parts, parts[1:]):
         assert a1 == b0
-    assert pkg.my_partition(10, 1) == [(0, 9)]
+    assert synth.my_partition(10, 1) == [(0, 9)]
 
 
-def test_spiral_recipe(pkg):
-    tra = pkg.spiral(40.0, 241, (50, 50), seed=0)
+def test_spiral_recipe(pkg, synth):
+    tra = synth.spiral(40.0, 241, (50, 50), seed=0)
     assert tra.shape == (241, 2) and tuple(tra[0]) == (50, 50)
     # uniform arc length: consecutive points are ~equidistant (jitter σ=1 per axis)
     d = np.linalg.norm(np.diff(tra, axis=0), axis=1)
     assert d.max() < 12 and np.abs(tra - 50).max() <= 40 + 6
-    np.testing.assert_array_equal(tra, pkg.spiral(40.0, 241, (50, 50), seed=0))   # seeded
-    assert not np.array_equal(tra, pkg.spiral(40.0, 241, (50, 50), seed=1))
-    ts, tr = pkg.build_trajectory(40.0, 24, (50, 50))
+    np.testing.assert_array_equal(tra, synth.spiral(40.0, 241, (50, 50), seed=0))   # seeded
+    assert not np.array_equal(tra, synth.spiral(40.0, 241, (50, 50), seed=1))
+    ts, tr = synth.build_trajectory(40.0, 24, (50, 50))
     assert len(ts) == 241 == len(tr) and ts[-1] == 10.0
 
 
-def test_synthetic_video_frames(pkg):
-    v = pkg.make_video(H=100, W=100, target_width=10, darker_target=True, start_ij=(50, 50))
+def test_synthetic_video_frames(pkg, synth):
+    v = synth.make_video(H=100, W=100, target_width=10, darker_target=True, start_ij=(50, 50))
     f = v.frame(0)
     assert f.dtype == np.uint8 and f.shape == (100, 100)
     assert f[49, 49] == 0 and f[0, 0] == 128 and (f == 0).sum() == 81           # filled disk of radius 5
-    v2 = pkg.make_video(H=100, W=200, target_width=10, darker_target=False, start_ij=(50, 100), sar=2)
+    v2 = synth.make_video(H=100, W=200, target_width=10, darker_target=False, start_ij=(50, 100), sar=2)
     f2 = v2.frame(0)
     assert f2.shape == (100, 100) and f2[49, 49] == 255 and v2.stored_centre(0) == (50, 50)
 
 
-def test_segment_length_mismatch_asserts(pkg):
-    v = pkg.make_video()
+def test_segment_length_mismatch_asserts(pkg, synth):
+    v = synth.make_video()
     with pytest.raises(AssertionError, match="Array length mismatch"):
         pkg.track_segments([v, v], start=[0.0], stop=[1.0, 1.0], start_location=[None, None])
 

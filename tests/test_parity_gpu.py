@@ -26,9 +26,11 @@ def disk_frame(H, W, cy, cx, r, val=0, bg=128):
     return f
 
 
-def check_step(pkg, oracle, frame, tw, darker, ws, guess, dense=True, check_map=True):
+def check_step(pkg, oracle, frame, tw, darker, ws, guess, dense=True, check_map=True, options=None):
     trk = pkg.Tracker(frame, tw, ws, darker)
     try:
+        for k_, v_ in (options or {}).items():
+            trk.set_option(k_, v_)
         ofill = oracle.mode(frame)
         assert trk.fillvalue == ofill
         ref = oracle.step(frame, ofill, tw, darker, ws, guess, dense=dense, want_map=check_map)
@@ -45,10 +47,11 @@ def check_step(pkg, oracle, frame, tw, darker, ws, guess, dense=True, check_map=
             assert rmap.shape == ref.R.shape
             err = np.abs(rmap.astype(np.float64) - ref.R).max()
             assert err <= tol, f"response map error {err / ref.maxabs:.3e} of max|R|"
-        if ref.near_tie(RTOL):
+        if ref.near_tie(RTOL) and ref.resp != ref.second:
             warnings.warn(f"documented near-tie: top-2 gap {(ref.resp - ref.second) / ref.maxabs:.2e} of max|R|; "
                           "argmax not compared")
         else:
+            # incl. EXACT ties (resp == second): findmax's first-in-column-major rule decides, in both implementations
             assert got_res == (ref.i, ref.j), (got_res, (ref.i, ref.j))
         return ref
     finally:
@@ -86,19 +89,18 @@ def test_config1_window_parity(gpu_pkg, oracle, cy, cx, guess):
     check_step(gpu_pkg, oracle, f, 25, True, (45, 45), guess)
 
 
-def test_generic_kernel_on_default_geometry(gpu_pkg, oracle, monkeypatch):
-    """The 45x45 / l=65 geometry normally dispatches to dog_window45_argmax; force the
+def test_generic_kernel_on_default_geometry(gpu_pkg, oracle):
+    """The 45x45 / l=65 geometry normally dispatches to the window45 kernels; force the
     generic streaming kernel on the same frames so both stay parity-checked."""
     f = disk_frame(480, 640, 200, 300, 12)
     b = gpu_pkg.TrackerBatch(1, f.shape, 25, (45, 45), True)
     assert b.kernel_name == "dog_window45_argmax"
-    b.close()
-    monkeypatch.setenv("PT_DISABLE_WINDOW45", "1")
-    b = gpu_pkg.TrackerBatch(1, f.shape, 25, (45, 45), True)
+    b.set_option("window45", 0)
     assert b.kernel_name.startswith("dog_rect_argmax_generic")
     b.close()
-    check_step(gpu_pkg, oracle, f, 25, True, (45, 45), (198, 305))
-    check_step(gpu_pkg, oracle, disk_frame(480, 640, 5, 630, 12), 25, True, (45, 45), (10, 625))
+    opts = {"window45": 0}
+    check_step(gpu_pkg, oracle, f, 25, True, (45, 45), (198, 305), options=opts)
+    check_step(gpu_pkg, oracle, disk_frame(480, 640, 5, 630, 12), 25, True, (45, 45), (10, 625), options=opts)
 
 
 @pytest.mark.parametrize("tw,ws,darker", [
@@ -179,12 +181,10 @@ def test_mode_kernel_tie_rule(gpu_pkg, oracle):
 
 
 @pytest.mark.parametrize("slow", [False, True])
-def test_mode_fast_and_slow_paths(gpu_pkg, oracle, monkeypatch, slow):
+def test_mode_fast_and_slow_paths(gpu_pkg, oracle, slow):
     """mode(frame): the counting pass (vector loads, lane-private histogram columns) decides alone unless two
-    values tie for the maximum count; then — and with PT_MODE_SLOW always — the last-position pass applies
+    values tie for the maximum count; then — and with option mode_slow always — the last-position pass applies
     StatsBase's rule.  Frame widths that are not multiples of 16, u8 and f32 pixels, several frames per batch."""
-    if slow:
-        monkeypatch.setenv("PT_MODE_SLOW", "1")
     rng = np.random.default_rng(8)
     for (H, W) in [(37, 53), (64, 64), (120, 200), (9, 1000)]:
         frames = [rng.integers(0, 256, (H, W)).astype(np.uint8),                       # noise: near-ties likely
@@ -194,6 +194,7 @@ def test_mode_fast_and_slow_paths(gpu_pkg, oracle, monkeypatch, slow):
         frames.append(tie)                                                             # exact tie (plus zeros if W odd)
         b = gpu_pkg.TrackerBatch(len(frames), (H, W), 10, (21, 21), True)
         try:
+            b.set_option("mode_slow", int(slow))
             b.set_frames(frames)
             got = b.compute_fill()
             assert [int(x) for x in got] == [oracle.mode(f) for f in frames], (H, W)
@@ -203,6 +204,7 @@ def test_mode_fast_and_slow_paths(gpu_pkg, oracle, monkeypatch, slow):
         f32 = [(f.astype(np.float32) / np.float32(255.0)) for f in frames]
         b = gpu_pkg.TrackerBatch(len(frames), (H, W), 10, (21, 21), True, dtype=np.float32)
         try:
+            b.set_option("mode_slow", int(slow))
             b.set_frames(f32)
             assert [int(x) for x in b.compute_fill()] == [oracle.mode(f) for f in frames], (H, W)
         finally:
@@ -275,7 +277,7 @@ def test_full_frame_rect_1080p(gpu_pkg, oracle):
 
 
 @pytest.mark.parametrize("chunks", ["1", "2", "3", "5", "99"])
-def test_marching_rect_kernel_chunkings(gpu_pkg, oracle, monkeypatch, chunks):
+def test_marching_rect_kernel_chunkings(gpu_pkg, oracle, chunks):
     """dog_rect45_march: a strip is cut into `chunks` runs of 45-row batches; inside a run the row-pass
     intermediate is carried from batch to batch.  Every chunking must give the same response map (bit for
     bit — the same operations in the same order) and that map must match the oracle; the window hangs over
@@ -283,9 +285,9 @@ def test_marching_rect_kernel_chunkings(gpu_pkg, oracle, monkeypatch, chunks):
     rng = np.random.default_rng(21)
     f = rng.integers(0, 256, (300, 280)).astype(np.uint8)
     ws, guess = (231, 200), (190, 60)           # 231x201 outputs = 6x5 tiles; rows 75..305, cols -40..160
-    monkeypatch.setenv("PT_R45_CHUNKS", chunks)
     trk = gpu_pkg.Tracker(f, 25, ws, False)
     try:
+        trk.set_option("r45_chunks", int(chunks))
         fill = oracle.mode(f)
         assert trk.fillvalue == fill
         ref = oracle.step(f, fill, 25, False, ws, guess, dense=False, want_map=True)
@@ -300,7 +302,7 @@ def test_marching_rect_kernel_chunkings(gpu_pkg, oracle, monkeypatch, chunks):
         # the published maximum is the maximum of the published map, at findmax's first position
         jj, ii = np.unravel_index(np.argmax(rmap.T), rmap.T.shape)
         assert resp == rmap[ii, jj]
-        monkeypatch.setenv("PT_R45_CHUNKS", "99")               # independent tiles
+        trk.set_option("r45_chunks", 99)                        # independent tiles
         assert np.array_equal(trk.response_map(guess), rmap)
     finally:
         trk.close()
@@ -344,12 +346,12 @@ def oracle_track(oracle, frames, tw, darker, ws, start_guess, autodetect=False):
     return np.array(out), near
 
 
-def test_config1_track_300_frames(gpu_pkg, oracle):
+def test_config1_track_300_frames(gpu_pkg, oracle, synth):
     """BASELINE config 1: 480×640, 300 frames, dark disk tw=25, start given, default window."""
     start = (240, 320)
     r = 0.8 * min(start[0], start[1], 480 - start[0], 640 - start[1])
-    tra = gpu_pkg.spiral(r, 300, start, seed=0)
-    vid = gpu_pkg.SyntheticVideo(480, 640, tra, 25, True, fps=24.0)
+    tra = synth.spiral(r, 300, start, seed=0)
+    vid = synth.SyntheticVideo(480, 640, tra, 25, True, fps=24.0)
     ts, ij = gpu_pkg.track(vid, start=0, stop=300 / 24.0, target_width=25,
                            start_location=gpu_pkg.CartesianIndex(*start), darker_target=True, fps=24)
     assert len(ts) == len(ij) == 300
@@ -362,9 +364,9 @@ def test_config1_track_300_frames(gpu_pkg, oracle):
     assert ts[0] == 0 and abs(ts[-1] - 300 / 24.0) < 1e-12
 
 
-def test_batch_equals_singles_and_all_paths_agree(gpu_pkg, oracle):
+def test_batch_equals_singles_and_all_paths_agree(gpu_pkg, oracle, synth):
     n, T, H, W = 6, 20, 240, 320
-    vids = [gpu_pkg.make_video(H=H, W=W, target_width=25, start_ij=(120, 160), seconds=10.0, fps=24.0, seed=s)
+    vids = [synth.make_video(H=H, W=W, target_width=25, start_ij=(120, 160), seconds=10.0, fps=24.0, seed=s)
             for s in range(n)]
     steps = [[v.frame(t) for v in vids] for t in range(T)]
     with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
@@ -398,12 +400,12 @@ def test_batch_equals_singles_and_all_paths_agree(gpu_pkg, oracle):
         np.testing.assert_array_equal(ij_fp[:, v], ref)
 
 
-def test_zero_copy_pinned_host_frames(gpu_pkg, oracle, monkeypatch):
+def test_zero_copy_pinned_host_frames(gpu_pkg, oracle, synth):
     """Pinned host frames: the chained kernel reads footprints over PCIe (zero-copy).  Must equal
     the staged footprint path (pageable frames) and the oracle loop, incl. windows leaving the frame."""
     import torch
     n, T, H, W = 5, 12, 200, 256
-    vids = [gpu_pkg.make_video(H=H, W=W, target_width=25, start_ij=(100, 128), seconds=10.0, fps=24.0, seed=10 + s)
+    vids = [synth.make_video(H=H, W=W, target_width=25, start_ij=(100, 128), seconds=10.0, fps=24.0, seed=10 + s)
             for s in range(n)]
     steps = [[v.frame(t) for v in vids] for t in range(T)]
     steps[3][0][:] = np.roll(steps[3][0], (-70, -100), axis=(0, 1))      # throw video 0 towards a corner
@@ -422,7 +424,7 @@ def test_zero_copy_pinned_host_frames(gpu_pkg, oracle, monkeypatch):
         ij_zc, r_zc = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
         assert b.launch_count - lc == 1, "pinned frames must take the single-launch zero-copy path"
         nxt, _ = b.step(None)                                          # chain state was left on the device
-        monkeypatch.setenv("PT_NO_ZEROCOPY", "1")
+        b.set_option("zero_copy", 0)
         b.set_guess(start)
         ij_staged, _ = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
     np.testing.assert_array_equal(ij_zc, ij_pageable)
@@ -433,9 +435,9 @@ def test_zero_copy_pinned_host_frames(gpu_pkg, oracle, monkeypatch):
         np.testing.assert_array_equal(ij_zc[:, v], ref)
 
 
-def test_track_autodetect_and_batch_api(gpu_pkg, oracle):
+def test_track_autodetect_and_batch_api(gpu_pkg, oracle, synth):
     """start_location = missing → auto-detect then track; track_batch == per-video track."""
-    vids = [gpu_pkg.make_video(H=240, W=320, target_width=25, start_ij=(120, 160), seconds=10.0, fps=24.0, seed=s)
+    vids = [synth.make_video(H=240, W=320, target_width=25, start_ij=(120, 160), seconds=10.0, fps=24.0, seed=s)
             for s in (3, 4)]
     singles = [gpu_pkg.track(v, stop=0.5, target_width=25, start_location=None, fps=24)[1] for v in vids]
     ts, ij = gpu_pkg.track_batch(vids, stop=0.5, target_width=25, start_location=None, fps=24)
@@ -447,14 +449,14 @@ def test_track_autodetect_and_batch_api(gpu_pkg, oracle):
         np.testing.assert_array_equal(singles[k], ref)
 
 
-def test_config2_1080p_autodetect_then_track(gpu_pkg, oracle):
+def test_config2_1080p_autodetect_then_track(gpu_pkg, oracle, synth):
     """BASELINE config 2 (shortened): one 1080p video, start_location = missing → auto-detect over the
     271×481 window centred on the frame (dog_rect45_march), then windowed tracking; positions identical to the
     oracle-driven loop and within 1 px RMS of the ground truth."""
     H, W, nfr = 1080, 1920, 60
     start = (540, 960)
-    tra = gpu_pkg.spiral(0.8 * 540, 3000, start, seed=0)[:nfr]          # the 3000-frame trajectory, first 60 frames
-    vid = gpu_pkg.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+    tra = synth.spiral(0.8 * 540, 3000, start, seed=0)[:nfr]          # the 3000-frame trajectory, first 60 frames
+    vid = synth.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
     ts, ij = gpu_pkg.track(vid, stop=nfr / 24.0, target_width=25, start_location=None, fps=24)
     assert len(ij) == nfr
     frames = [vid.frame(k) for k in range(nfr)]
@@ -464,15 +466,15 @@ def test_config2_1080p_autodetect_then_track(gpu_pkg, oracle):
     assert np.sqrt(np.mean(np.sum((ij - tra) ** 2, axis=1))) < 1.0
 
 
-def test_config5_segments_sar_start_fps(gpu_pkg, oracle):
+def test_config5_segments_sar_start_fps(gpu_pkg, oracle, synth):
     """Segmented multi-file video, SAR=2, (x,y) start, non-zero start, fps resampling
     (test/test-basic-test.jl:43-49, 73-79, 91-104, 116-121; src/PawsomeTracker.jl:181-214)."""
     H, Wd, sar, src_fps, fps = 270, 960, 2, 24.0, 12.0
     start_disp = (135, 480)                                          # displayed (row, col)
     r = 0.8 * min(start_disp[0], start_disp[1], H - start_disp[0], Wd - start_disp[1])
-    _, tra = gpu_pkg.build_trajectory(r, src_fps, start_disp, seconds=12.0, seed=0)    # 289 source frames
-    parts = gpu_pkg.my_partition(len(tra), 3)
-    segs = [gpu_pkg.SyntheticVideo(H, Wd, tra[a:b + 1], 25, True, fps=src_fps, sar=sar) for a, b in parts]
+    _, tra = synth.build_trajectory(r, src_fps, start_disp, seconds=12.0, seed=0)    # 289 source frames
+    parts = synth.my_partition(len(tra), 3)
+    segs = [synth.SyntheticVideo(H, Wd, tra[a:b + 1], 25, True, fps=src_fps, sar=sar) for a, b in parts]
     seg_start = [0.25, 0.0, 0.0]
     seg_stop = [(b - a + 1) / src_fps for a, b in parts]
     x0 = int(tra[parts[0][0] + 6, 1]); y0 = int(tra[parts[0][0] + 6, 0])      # where the target is at t=0.25 s
@@ -507,14 +509,14 @@ def test_config5_segments_sar_start_fps(gpu_pkg, oracle):
     assert rmse < 1.5, rmse        # column quantisation by SAR=2 adds up to 1 px
 
 
-def test_segment_parallel_equals_serial(gpu_pkg):
+def test_segment_parallel_equals_serial(gpu_pkg, synth):
     """segments that bring their own start_location start independent chains which advance
     concurrently in one batch; the result must equal the reference-order serial loop (:202-206), including
     per-segment fills, the first-frame refinement, an auto-detected first segment and unequal segment lengths."""
     H, W, fps = 240, 320, 24.0
-    _, tra = gpu_pkg.build_trajectory(0.8 * 120, fps, (120, 160), seconds=6.0, seed=5)
-    parts = gpu_pkg.my_partition(len(tra), 5)
-    segs = [gpu_pkg.SyntheticVideo(H, W, tra[a:b + 1], 25, True, fps=fps) for a, b in parts]
+    _, tra = synth.build_trajectory(0.8 * 120, fps, (120, 160), seconds=6.0, seed=5)
+    parts = synth.my_partition(len(tra), 5)
+    segs = [synth.SyntheticVideo(H, W, tra[a:b + 1], 25, True, fps=fps) for a, b in parts]
     fr3 = np.stack([segs[3].frame(k) for k in range(len(segs[3]))])
     fr3[fr3 == 128] = 140                                                  # another background: the fill differs per segment
     segs[3] = gpu_pkg.ArrayVideo(fr3, fps=fps)
@@ -610,7 +612,7 @@ def test_batch_sizes_exercise_cta_video_loop(gpu_pkg, oracle, n, T):
 
 
 @pytest.mark.parametrize("dtype", [np.uint8, np.float32])
-def test_rotating_slots_equal_static_split(gpu_pkg, monkeypatch, dtype):
+def test_rotating_slots_equal_static_split(gpu_pkg, dtype):
     """dog_window45_rot vs dog_window45_argmax on the same 240-video, 11-step chain: identical positions AND
     bit-identical responses (same arithmetic, only the SM a window runs on changes); hand-off scratch left clean
     (a second chained call gives the same answer)."""
@@ -628,20 +630,22 @@ def test_rotating_slots_equal_static_split(gpu_pkg, monkeypatch, dtype):
         ij_rot, r_rot = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
         b.set_guess(start)
         ij_rot2, r_rot2 = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
-        monkeypatch.setenv("PT_W45_ROT", "0")
+        assert b.last_kernel == "dog_window45_rot"
+        b.set_option("rot", 0)
         b.set_guess(start)
         ij_st, r_st = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_argmax"
     np.testing.assert_array_equal(ij_rot, ij_st)
     np.testing.assert_array_equal(r_rot, r_st)
     np.testing.assert_array_equal(ij_rot2, ij_st)
     np.testing.assert_array_equal(r_rot2, r_st)
 
 
-def test_float32_frames_chained_and_batched(gpu_pkg, oracle):
+def test_float32_frames_chained_and_batched(gpu_pkg, oracle, synth):
     """f32 frames through the chained (resident) path of the specialised kernel."""
     import torch
     n, T, H, W = 5, 6, 150, 170
-    vids = [gpu_pkg.make_video(H=H, W=W, target_width=25, start_ij=(75, 85), seconds=10.0, fps=24.0, seed=40 + s)
+    vids = [synth.make_video(H=H, W=W, target_width=25, start_ij=(75, 85), seconds=10.0, fps=24.0, seed=40 + s)
             for s in range(n)]
     f8 = np.stack([np.stack([v.frame(t) for v in vids]) for t in range(T)])
     f32 = f8.astype(np.float32) / np.float32(255.0)
@@ -673,14 +677,14 @@ def test_guess_far_outside_frame(gpu_pkg, oracle):
             trk.close()
 
 
-def test_host_decode_feeder_cv2(gpu_pkg, tmp_path):
+def test_host_decode_feeder_cv2(gpu_pkg, tmp_path, synth):
     """SURVEY §8(f) rank 1 ("next"): a real video file decoded on the host (OpenCV/FFmpeg → GRAY8, the role of
     `openvideo(…, AV_PIX_FMT_GRAY8)`, src/PawsomeTracker.jl:157) feeding track().  The codec is lossy, so the
     bar is the reference's behavioural one: RMSE < 1 px against the ground truth (README.md:24)."""
     cv2 = pytest.importorskip("cv2")
     H, W, nfr = 240, 320, 48
-    tra = gpu_pkg.spiral(0.8 * 120, 600, (120, 160), seed=3)[:nfr]
-    vid = gpu_pkg.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+    tra = synth.spiral(0.8 * 120, 600, (120, 160), seed=3)[:nfr]
+    vid = synth.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
     path = str(tmp_path / "clip.avi")
     wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 24.0, (W, H), isColor=True)
     if not wr.isOpened():
@@ -698,7 +702,7 @@ def test_host_decode_feeder_cv2(gpu_pkg, tmp_path):
     assert np.abs(ij2[0] - tra[0]).max() <= 1
 
 
-def test_decode_feeder_pinned_ring_batch(gpu_pkg, tmp_path):
+def test_decode_feeder_pinned_ring_batch(gpu_pkg, tmp_path, synth):
     """several encoded files decoded concurrently by host threads into the ring of page-locked
     step-chunks (FrameFeeder) and tracked in one batch with zero-copy footprint reads; decoding is deterministic, so
     the batch must reproduce the per-file `track` exactly — including a file that is shorter than the others."""
@@ -706,8 +710,8 @@ def test_decode_feeder_pinned_ring_batch(gpu_pkg, tmp_path):
     H, W, nfr = 240, 320, 40
     paths, tras = [], []
     for s_ in range(5):
-        tra = gpu_pkg.spiral(0.8 * 120, 600, (120, 160), seed=20 + s_)[:nfr - (7 if s_ == 3 else 0)]
-        vid = gpu_pkg.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+        tra = synth.spiral(0.8 * 120, 600, (120, 160), seed=20 + s_)[:nfr - (7 if s_ == 3 else 0)]
+        vid = synth.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
         path = str(tmp_path / f"clip{s_}.avi")
         wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 24.0, (W, H), isColor=True)
         if not wr.isOpened():
@@ -730,7 +734,7 @@ def test_decode_feeder_pinned_ring_batch(gpu_pkg, tmp_path):
     pa.close()
 
 
-def test_diagnostic_video_and_device_downscale(gpu_pkg, tmp_path):
+def test_diagnostic_video_and_device_downscale(gpu_pkg, tmp_path, synth):
     """`diagnostic_file` (src/diagnose.jl): one 360x640 frame per tracked frame with the
     frame downscaled on the device, dot and trail at the tracked point.  The downscale kernel is checked against
     the bilinear formula it implements (pixel-centre aligned; the reference's ImageTransformations is not vendored)."""
@@ -755,8 +759,8 @@ def test_diagnostic_video_and_device_downscale(gpu_pkg, tmp_path):
         assert np.abs(got[v].astype(np.float64) - ref).max() <= 0.5 + 1e-3
     # the diagnostics video of a short track
     nfr = 20
-    tra = gpu_pkg.spiral(0.8 * 135, 600, (135, 240), seed=1)[:nfr]
-    vid = gpu_pkg.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+    tra = synth.spiral(0.8 * 135, 600, (135, 240), seed=1)[:nfr]
+    vid = synth.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
     out = str(tmp_path / "diag.avi")
     ts, ij = gpu_pkg.track(vid, stop=nfr / 24.0, target_width=25, start_location=gpu_pkg.CartesianIndex(135, 240),
                            fps=24, diagnostic_file=out)

@@ -1,0 +1,515 @@
+"""GPU parity tests, round 2: the gaps the round-1 review listed.
+
+  * BASELINE configs 2 and 3 at FULL size against the oracle (3000-frame 1080p track with auto-detect start; 256 x
+    1080p videos x 20 chained steps through dog_window45_rot and the static split, positions exact, responses within
+    RTOL·max|R|);
+  * exact ties: periodic frames give bit-identical responses at lattice-equivalent positions in the f64 oracle and in
+    the FP32 kernels (translation-invariant arithmetic), so findmax's rule — first maximum in column-major order,
+    src/PawsomeTracker.jl:59 — is checked across warps, halves, strips, chunks, CTAs and cluster ranks;
+  * the lone-window cluster kernel (dog_window45_cluster<C>) in every staging mode against the per-SM kernel
+    (bit-identical responses) and the oracle;
+  * responses (not only positions) on the chained paths;
+  * handles driven concurrently from several host threads / on several devices.
+"""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def disk_frame(H, W, cy, cx, r, val=0, bg=128):
+    f = np.full((H, W), bg, np.uint8)
+    yy, xx = np.ogrid[0:H, 0:W]
+    f[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = val
+    return f
+
+
+def oracle_chain(oracle, frames, tw, darker, ws, start_guess, fill=None):
+    """ij[t] = trckr(ij[t-1]) driven by the oracle (dense f64, reference loop order).
+    Returns positions (T,2), responses (T,), max|R| (T,), number of near-ties."""
+    fill = oracle.mode(frames[0]) if fill is None else fill
+    g = tuple(int(x) for x in start_guess)
+    pos, resp, mx, near = [], [], [], 0
+    for f in frames:
+        r = oracle.step(f, fill, tw, darker, ws, g, dense=True)
+        near += r.near_tie(RTOL)
+        g = (r.i, r.j)
+        pos.append(g); resp.append(r.resp); mx.append(r.maxabs)
+    return np.array(pos), np.array(resp), np.array(mx), near
+
+
+# ---------------------------------------------------------------------------
+# lone-window cluster kernel
+# ---------------------------------------------------------------------------
+def _cluster_case(synth, H, W, n, T, seed):
+    vids = [synth.make_video(H=H, W=W, target_width=25, start_ij=(H // 2, W // 2), seconds=10.0, fps=24.0, seed=seed + s)
+            for s in range(n)]
+    frames = np.stack([np.stack([v.frame(t) for v in vids]) for t in range(T)])          # (T, n, H, W)
+    frames[3, 0] = np.roll(frames[3, 0], (-(H // 2 - 30), -(W // 2 - 40)), axis=(0, 1))  # throw video 0 towards a corner
+    start = np.tile([H // 2, W // 2], (n, 1)).astype(np.int32)
+    if n > 1:
+        start[1] = (-30, W + 25)          # a guess outside the frame: clamped result leaves the prefetched region
+    return frames, start
+
+
+@pytest.mark.parametrize("C", [2, 4, 8])
+@pytest.mark.parametrize("bulk", [0, 1, 2])
+def test_cluster_kernel_equals_per_sm_kernel_and_oracle(gpu_pkg, oracle, synth, C, bulk):
+    """One window over a cluster of C CTAs (column slices, argmax through DSMEM) with global-load staging (0),
+    cp.async.bulk rows (1) or one TMA tile per step (2): positions AND responses bit-identical to
+    dog_window45_argmax (same per-output operation order), positions equal to the oracle loop."""
+    import torch
+    n, T, H, W = 5, 9, 200, 256
+    frames, start = _cluster_case(synth, H, W, n, T, 100)
+    dev = torch.from_numpy(frames).cuda()
+    with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        fills = b.compute_fill()
+        b.set_option("cluster", 1)
+        b.set_guess(start)
+        ij0, r0 = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_argmax"
+        b.set_option("cluster", C); b.set_option("bulk", bulk)
+        b.set_guess(start)
+        ij1, r1 = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == f"dog_window45_cluster<{C}>"
+        b.set_guess(start)
+        ij2, r2 = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)          # scratch / barriers left clean
+        # the single-step entry point runs the same kernel with T = 1
+        b.set_guess(start)
+        per_step = []
+        for t in range(T):
+            b.bind_device_frames(dev.data_ptr() + t * n * H * W, H * W, W)
+            o, rr = b.step(None)
+            per_step.append((o.copy(), rr.copy()))
+    np.testing.assert_array_equal(ij1, ij0)
+    np.testing.assert_array_equal(r1, r0)
+    np.testing.assert_array_equal(ij2, ij0)
+    np.testing.assert_array_equal(r2, r0)
+    np.testing.assert_array_equal(np.stack([p[0] for p in per_step]), ij0)
+    np.testing.assert_array_equal(np.stack([p[1] for p in per_step]), r0)
+    for v in range(n):
+        pos, resp, mx, near = oracle_chain(oracle, [frames[t, v] for t in range(T)], 25, True, (45, 45), start[v], int(fills[v]))
+        if near == 0:
+            np.testing.assert_array_equal(ij1[:, v], pos)
+            assert np.all(np.abs(r1[:, v] - resp) <= RTOL * mx)
+
+
+@pytest.mark.parametrize("C", [2, 4, 8])
+def test_cluster_kernel_f32_and_unaligned_frames(gpu_pkg, oracle, synth, C):
+    """f32 frames and u8 frames whose rows are not 16-byte aligned cannot use the TMA staging: the cluster kernel
+    stages them with global loads; same results as the per-SM kernel."""
+    import torch
+    n, T, H, W = 3, 6, 150, 170                                  # pitch 170: not a multiple of 16
+    frames, start = _cluster_case(synth, H, W, n, T, 300)
+    for dtype in (np.uint8, np.float32):
+        fr = frames if dtype is np.uint8 else frames.astype(np.float32) / np.float32(255.0)
+        pitch = W
+        if dtype is np.uint8:                                    # 4-byte aligned rows are the u8 kernels' requirement
+            pitch = 172
+            padded = np.zeros((T, n, H, pitch), np.uint8); padded[..., :W] = fr; fr = padded
+        dev = torch.from_numpy(fr).cuda()
+        with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True, dtype=dtype) as b:
+            b.bind_device_frames(dev.data_ptr(), H * pitch, pitch)
+            b.compute_fill()
+            b.set_option("cluster", 1); b.set_guess(start)
+            ij0, r0 = b.track_device(dev.data_ptr(), n * H * pitch, H * pitch, pitch, T)
+            b.set_option("cluster", C); b.set_guess(start)
+            ij1, r1 = b.track_device(dev.data_ptr(), n * H * pitch, H * pitch, pitch, T)
+            assert b.last_kernel == f"dog_window45_cluster<{C}>"
+        np.testing.assert_array_equal(ij1, ij0)
+        np.testing.assert_array_equal(r1, r0)
+
+
+def test_cluster_size_policy(gpu_pkg):
+    """Auto policy: as many CTAs per window as fit one per SM (8, 4, 2), the per-SM kernels from #SMs/2 windows up."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    H, W, T = 64, 64, 2
+    for n in (1, sms // 8, sms // 8 + 1, sms // 4, sms // 4 + 1, sms // 2, sms // 2 + 1, sms):
+        dev = torch.full((T, n, H, W), 128, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
+            b.set_fill(128); b.set_guess(np.tile([32, 32], (n, 1)))
+            b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+            want = ("dog_window45_cluster<8>" if 8 * n <= sms else "dog_window45_cluster<4>" if 4 * n <= sms else
+                    "dog_window45_cluster<2>" if 2 * n <= sms else "dog_window45_argmax")
+            assert b.last_kernel == want, (n, b.last_kernel)
+
+
+# ---------------------------------------------------------------------------
+# exact ties: findmax's first-in-column-major rule (src/PawsomeTracker.jl:59)
+# ---------------------------------------------------------------------------
+def periodic_frame(H, W, py, px, seed):
+    rng = np.random.default_rng(seed)
+    tile = rng.integers(90, 166, (py, px)).astype(np.uint8)
+    reps = (H + py - 1) // py, (W + px - 1) // px
+    return np.tile(tile, reps)[:H, :W].copy()
+
+
+def _first_colmajor_max(rmap):
+    m = rmap.max()
+    jj, ii = np.nonzero(rmap.T == m)            # transposed: first hit in column-major order
+    return int(ii[0]), int(jj[0]), len(ii)
+
+
+def _check_exact_tie(trk, oracle, f, tw, darker, ws, guess, dense, min_ties):
+    fill = oracle.mode(f)
+    assert trk.fillvalue == fill
+    ref = oracle.step(f, fill, tw, darker, ws, guess, dense=dense, want_map=True)
+    assert ref.resp == ref.second, "the oracle does not see an exact tie: the test frame is wrong"
+    oi, oj, ocount = _first_colmajor_max(ref.R)
+    assert ocount >= min_ties
+    rr, rc = ws[0] // 2, ws[1] // 2
+    assert (ref.raw_i, ref.raw_j) == (guess[0] - rr + oi, guess[1] - rc + oj)      # the oracle follows findmax
+    got = trk.step_resident(guess)
+    resp = trk.last_response
+    rmap = trk.response_map(guess)
+    gi, gj, gcount = _first_colmajor_max(rmap)
+    assert gcount == ocount, "tied maxima must be bit-identical in the FP32 kernels too"
+    assert (gi, gj) == (oi, oj)
+    assert got == (ref.i, ref.j)
+    assert resp == rmap[gi, gj]
+    assert abs(resp - ref.resp) <= RTOL * ref.maxabs
+    return got
+
+
+@pytest.mark.parametrize("period", [(15, 15), (9, 20), (22, 7)])
+@pytest.mark.parametrize("variant", ["argmax", "cluster2", "cluster4", "cluster8", "generic"])
+def test_exact_ties_in_the_45_window(gpu_pkg, oracle, period, variant):
+    """A frame that is periodic with period (py, px) has a periodic response: several bit-identical maxima inside
+    one 45x45 window, in different warps / halves (per-SM kernel), cluster ranks (cluster kernel) or strips and
+    row groups (generic kernel).  GPU == oracle == smallest column-major index among the maxima."""
+    f = periodic_frame(260, 288, period[0], period[1], seed=period[0] * 31 + period[1])
+    trk = gpu_pkg.Tracker(f, 25, (45, 45), True)
+    try:
+        if variant == "generic":
+            trk.set_option("window45", 0)
+        elif variant == "argmax":
+            trk.set_option("cluster", 1)
+        else:
+            trk.set_option("cluster", int(variant[-1]))
+        min_ties = (45 // period[0]) * (45 // period[1])
+        got = _check_exact_tie(trk, oracle, f, 25, True, (45, 45), (131, 140), True, min_ties)
+        # the footprint path (crop uploaded, same kernel) must take the same decision
+        assert trk((131, 140)) == got
+    finally:
+        trk.close()
+
+
+@pytest.mark.parametrize("chunks", [0, 1, 2, 99])
+def test_exact_ties_across_strips_and_chunks_of_the_marching_kernel(gpu_pkg, oracle, chunks):
+    """dog_rect45_march on a 135x181 window of a frame with period (45, 60): tied maxima fall into different
+    45-column strips, different chunks of a strip and different CTAs; the 64-bit atomicMax merge must keep the
+    smallest column-major index."""
+    f = periodic_frame(420, 460, 45, 60, seed=5)
+    ws, guess = (135, 181), (210, 230)
+    trk = gpu_pkg.Tracker(f, 25, ws, False)
+    try:
+        trk.set_option("r45_chunks", chunks)
+        _check_exact_tie(trk, oracle, f, 25, False, ws, guess, True, 9)
+    finally:
+        trk.close()
+
+
+@pytest.mark.parametrize("tw,ws,period", [(10, (75, 99), (25, 33)), (40, (97, 65), (32, 32))])
+def test_exact_ties_across_ctas_of_the_generic_kernel(gpu_pkg, oracle, tw, ws, period):
+    """Generic kernel (l != 65): strips of 32 columns, row chunks, one atomicMax per CTA."""
+    l = oracle.kernel_len(tw)
+    H, W = ws[0] + l + 40, ws[1] + l + 40
+    f = periodic_frame(H, W, period[0], period[1], seed=tw)
+    guess = (H // 2, W // 2)
+    trk = gpu_pkg.Tracker(f, tw, ws, True)
+    try:
+        min_ties = (ws[0] // period[0]) * (ws[1] // period[1])
+        _check_exact_tie(trk, oracle, f, tw, True, ws, guess, True, min_ties)
+    finally:
+        trk.close()
+
+
+def test_exact_ties_in_a_batch_through_rot_and_static(gpu_pkg, oracle):
+    """Chained batch (static split and rotating slots): every video sees a periodic frame sequence, so every step
+    is an exact tie; positions must follow the oracle loop (findmax rule at every step)."""
+    import torch
+    n, T, H, W = 200, 4, 255, 288                        # 17 x 15 rows, 18 x 16 columns: periodic across the wrap of np.roll
+    base = [periodic_frame(H, W, 15, 16, seed=s) for s in range(4)]
+    frames = np.stack([np.stack([np.roll(base[(v + t) % 4], (v % 7, (3 * v) % 11), axis=(0, 1)) for v in range(n)])
+                       for t in range(T)])
+    dev = torch.from_numpy(frames).cuda()
+    # the first maximum sits in the top-left period cell of the window, so a window drifts by up to 22 px per step:
+    # started at the centre, the footprints of all four steps stay inside the frame (no border fill, exact periodicity)
+    start = np.tile([130, 144], (n, 1))
+    with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        fills = b.compute_fill()
+        b.set_guess(start)
+        ij_rot, r_rot = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_rot"
+        b.set_option("rot", 0); b.set_guess(start)
+        ij_st, r_st = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+    np.testing.assert_array_equal(ij_rot, ij_st)
+    np.testing.assert_array_equal(r_rot, r_st)
+    for v in (0, 1, 57, 147, 148, 199):
+        g = (130, 144)
+        for t in range(T):
+            r = oracle.step(frames[t, v], int(fills[v]), 25, True, (45, 45), g, dense=True)
+            assert r.resp == r.second                      # an exact tie at every step
+            assert tuple(ij_st[t, v]) == (r.i, r.j), (v, t)
+            assert abs(r_st[t, v] - r.resp) <= RTOL * r.maxabs
+            g = (r.i, r.j)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs at full size
+# ---------------------------------------------------------------------------
+def test_config2_full_3000_frames_1080p(gpu_pkg, oracle, synth):
+    """BASELINE config 2 as written: one 1080p video, 3000 frames, start_location = missing (auto-detect window
+    size .÷ 4, src/PawsomeTracker.jl:99-105) then windowed tracking — through the public track(); every position
+    identical to the oracle-driven loop (dense f64 in the reference's order), RMSE < 1 px (README.md:24)."""
+    H, W, nfr = 1080, 1920, 3000
+    start = (540, 960)
+    tra = synth.spiral(0.8 * 540, nfr, start, seed=0)
+    vid = synth.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+    ts, ij = gpu_pkg.track(vid, stop=nfr / 24.0, target_width=25, start_location=None, fps=24)
+    assert len(ij) == nfr and len(ts) == nfr
+    f0 = vid.frame(0)
+    fill = oracle.mode(f0)
+    r = oracle.step(f0, fill, 25, True, (H // 4, W // 4), (H // 2, W // 2), dense=False)
+    assert not r.near_tie(RTOL)
+    g = (r.i, r.j)
+    assert tuple(ij[0]) == g
+    buf = np.empty((H, W), np.uint8)
+    near = 0
+    for k in range(1, nfr):
+        f = vid.frame(k, buf)
+        r = oracle.step(f, fill, 25, True, (45, 45), g, dense=True)
+        near += r.near_tie(RTOL)
+        g = (r.i, r.j)
+        assert tuple(ij[k]) == g, k
+    assert near == 0
+    assert np.sqrt(np.mean(np.sum((ij - tra) ** 2, axis=1))) < 1.0
+
+
+def test_config3_full_size_256_videos_vs_oracle(gpu_pkg, oracle):
+    """BASELINE config 3 at full size: 256 x 1080p videos x 20 chained steps, resident in HBM, through
+    dog_window45_rot AND the static split: every (video, step) position equal to the oracle's (the oracle advances
+    all videos of a step on all host threads), responses within RTOL, both kernels bit-identical."""
+    import torch
+    import bench
+    n, T, H, W = 256, 20, 1080, 1920
+    pos = bench.orbit_positions(n, 4242)
+    rng = np.random.default_rng(7)
+    dev = torch.device("cuda", 0)
+    ring = bench.render_ring_device(torch, pos, T, dev)                       # (T, n, H, W) u8, 10.6 GB
+    # a different disk darkness per video (0..49 on the 128 background) so that the responses differ between videos
+    for v in range(n):
+        ring[:, v].clamp_(min=v % 50)
+    torch.cuda.synchronize()
+    start = pos[0] + rng.integers(-6, 7, (n, 2))
+    with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
+        b.bind_device_frames(ring.data_ptr(), H * W, W)
+        fills = b.compute_fill()
+        b.set_guess(start)
+        ij_rot, r_rot = b.track_device(ring.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_rot"
+        b.set_option("rot", 0); b.set_guess(start)
+        ij_st, r_st = b.track_device(ring.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_argmax"
+    np.testing.assert_array_equal(ij_rot, ij_st)
+    np.testing.assert_array_equal(r_rot, r_st)
+    g = start.astype(np.int32)
+    for t in range(T):
+        host = ring[t].cpu().numpy()
+        out, resp, _ = oracle.batch_step_dense([host[v] for v in range(n)], fills, 25, True, (45, 45), g, nthreads=0)
+        np.testing.assert_array_equal(ij_rot[t], out, err_msg=f"step {t}")
+        assert np.all(np.abs(r_rot[t] - resp) <= RTOL * np.abs(resp)), t          # max|R| >= |resp|: a stricter bar
+        g = out
+    np.testing.assert_array_equal(ij_rot, bench.truth_for_steps(pos, T))
+
+
+def test_chained_paths_responses_match_oracle(gpu_pkg, oracle, synth):
+    """Responses — not only positions — on every chained path (resident, zero-copy pinned, staged footprint,
+    whole frames): within RTOL·max|R| of the oracle loop at every step."""
+    import torch
+    n, T, H, W = 4, 10, 240, 320
+    vids = [synth.make_video(H=H, W=W, target_width=25, start_ij=(120, 160), seconds=10.0, fps=24.0, seed=70 + s)
+            for s in range(n)]
+    rng = np.random.default_rng(3)
+    steps = [[np.clip(v.frame(t).astype(int) + rng.integers(-5, 6, (H, W)), 0, 255).astype(np.uint8) for v in vids]
+             for t in range(T)]
+    start = np.tile([120, 160], (n, 1))
+    pinned = torch.empty((T, n, H, W), dtype=torch.uint8, pin_memory=True)
+    pnp = pinned.numpy()
+    for t in range(T):
+        for v in range(n):
+            pnp[t, v] = steps[t][v]
+    dev = pinned.cuda()
+    res = {}
+    with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
+        b.set_frames(steps[0]); fills = b.compute_fill()
+        b.set_guess(start); res["staged"] = b.track_host(steps, mode="footprint")
+        b.set_guess(start); res["frames"] = b.track_host(steps, mode="frames")
+        b.set_guess(start); res["zero-copy"] = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+        for c in (1, 4):
+            b.set_option("cluster", c)
+            b.set_guess(start); res[f"resident/cluster={c}"] = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+    for v in range(n):
+        pos, resp, mx, near = oracle_chain(oracle, [s[v] for s in steps], 25, True, (45, 45), start[v], int(fills[v]))
+        assert near == 0
+        for name, (ij, r) in res.items():
+            np.testing.assert_array_equal(ij[:, v], pos, err_msg=name)
+            assert np.all(np.abs(r[:, v] - resp) <= RTOL * mx), name
+
+
+# ---------------------------------------------------------------------------
+# concurrency: distinct handles from distinct host threads / devices (SURVEY §8b threading)
+# ---------------------------------------------------------------------------
+def _thread_job(pkg, device, frames, start, T, reps, out, idx, errs, options):
+    try:
+        import torch
+        n, H, W = frames.shape[1:]
+        with torch.cuda.device(device):
+            dev = torch.from_numpy(frames).to(f"cuda:{device}")
+            torch.cuda.synchronize(device)
+            got = []
+            for _ in range(reps):
+                with pkg.TrackerBatch(n, (H, W), 25, (45, 45), True, device=device) as b:
+                    for k_, v_ in options.items():
+                        b.set_option(k_, v_)
+                    b.bind_device_frames(dev.data_ptr(), H * W, W)
+                    b.compute_fill()
+                    b.set_guess(start)
+                    ij, r = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+                    b.set_guess(start)
+                    ij_h, r_h = b.track_host([[frames[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+                    got.append((ij.copy(), r.copy(), ij_h.copy(), r_h.copy()))
+            out[idx] = got
+    except BaseException as e:      # noqa: BLE001
+        errs.append(repr(e))
+
+
+def test_two_handles_from_two_host_threads(gpu_pkg, synth):
+    """Two (and four) host threads, each creating, driving and destroying its own batches on device 0 at the same
+    time — the per-SM kernel, the cooperative rot kernel, the cluster kernel and the multi-lane pageable footprint
+    path all in flight together.  Results must equal the same jobs run one after the other."""
+    T = 6
+    jobs = []
+    for k, (n, opts) in enumerate([(150, {}), (3, {}), (190, {"rot": 2}), (9, {"cluster": 4})]):
+        vids = [synth.make_video(H=120, W=160, target_width=25, start_ij=(60, 80), seconds=10.0, fps=24.0, seed=500 + 50 * k + s)
+                for s in range(n)]
+        frames = np.stack([np.stack([v.frame(t) for v in vids]) for t in range(T)])
+        jobs.append((frames, np.tile([60, 80], (n, 1)), opts))
+    serial = [None] * len(jobs)
+    errs = []
+    for i, (fr, st, opts) in enumerate(jobs):
+        _thread_job(gpu_pkg, 0, fr, st, T, 1, serial, i, errs, opts)
+    assert not errs, errs
+    for nthreads in (2, 4):
+        conc = [None] * nthreads
+        th = [threading.Thread(target=_thread_job, args=(gpu_pkg, 0, jobs[i][0], jobs[i][1], T, 3, conc, i, errs, jobs[i][2]))
+              for i in range(nthreads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs, errs
+        for i in range(nthreads):
+            for rep in conc[i]:
+                for a, b_ in zip(rep, serial[i][0]):
+                    np.testing.assert_array_equal(a, b_)
+
+
+def test_handles_on_two_devices_in_one_process(gpu_pkg, synth):
+    """pt_batch_create(..., device, ...): per-device state (shared-memory opt-ins, SM count) is keyed by device.
+    Runs only where the box has two GPUs."""
+    if gpu_pkg.lib.pt_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    T, n = 5, 160
+    vids = [synth.make_video(H=120, W=160, target_width=25, start_ij=(60, 80), seconds=10.0, fps=24.0, seed=900 + s)
+            for s in range(n)]
+    frames = np.stack([np.stack([v.frame(t) for v in vids]) for t in range(T)])
+    start = np.tile([60, 80], (n, 1))
+    out, errs = [None, None], []
+    th = [threading.Thread(target=_thread_job, args=(gpu_pkg, d, frames, start, T, 2, out, d, errs, {})) for d in (0, 1)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for a, b_ in zip(out[0][0], out[1][0]):
+        np.testing.assert_array_equal(a, b_)
+
+
+# ---------------------------------------------------------------------------
+# f1 / f4: real files with start > 0, fps != native, shorter stop; oracle on the decoded frames; downscale pinned
+# ---------------------------------------------------------------------------
+def _write_mjpg(cv2, path, vid, nfr, W, H, fps):
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), fps, (W, H), isColor=True)
+    if not wr.isOpened():
+        pytest.skip("OpenCV cannot write MJPG/AVI in this build")
+    for k in range(nfr):
+        wr.write(cv2.cvtColor(vid.frame(k), cv2.COLOR_GRAY2BGR))
+    wr.release()
+
+
+def _decode_all(cv2, path):
+    cap = cv2.VideoCapture(path)
+    out = []
+    while True:
+        ok, bgr = cap.read()
+        if not ok:
+            break
+        out.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    return out
+
+
+@pytest.mark.parametrize("start,stop,fps", [(0.0, 2.0, 24), (0.5, 1.75, 24), (0.25, 2.0, 12), (1.0, 60.0, 8)])
+def test_real_file_track_equals_oracle_on_decoded_frames(gpu_pkg, oracle, synth, tmp_path, start, stop, fps):
+    """`ffmpeg -ss start -i file -t t -vf fps=fps` (src/PawsomeTracker.jl:155) on a real container: track(path)
+    must equal the oracle loop run on the frames OpenCV decodes (decode is deterministic), for a non-zero start, a
+    shorter stop, an fps that differs from the file's, and a stop beyond the end of the file (EOF guard, :162)."""
+    cv2 = pytest.importorskip("cv2")
+    H, W, nfr, src_fps = 240, 320, 60, 24.0
+    tra = synth.spiral(0.8 * 120, 600, (120, 160), seed=33)[:nfr]
+    vid = synth.SyntheticVideo(H, W, tra, 25, True, fps=src_fps)
+    path = str(tmp_path / "clip.avi")
+    _write_mjpg(cv2, path, vid, nfr, W, H, src_fps)
+    decoded = _decode_all(cv2, path)
+    assert len(decoded) == nfr
+    n = int(round(fps * (stop - start)))
+    idx = [int(np.floor((start + k / fps) * src_fps + 0.5)) for k in range(n)]
+    idx = [i for i in idx if i < nfr]
+    first = idx[0]
+    loc = gpu_pkg.CartesianIndex(int(tra[first, 0]) + 2, int(tra[first, 1]) - 3)
+    ts, ij = gpu_pkg.track(path, start=start, stop=stop, target_width=25, start_location=loc, fps=fps)
+    assert len(ij) == len(idx) == len(ts)
+    pos, _, _, near = oracle_chain(oracle, [decoded[i] for i in idx], 25, True, (45, 45), (loc.i, loc.j))
+    assert near == 0
+    np.testing.assert_array_equal(ij, pos)
+    assert np.sqrt(np.mean(np.sum((ij - tra[idx]) ** 2, axis=1))) < 1.0
+    assert ts[0] == start
+    # the batched feeder path on the same file (twice) takes the same decisions
+    _, ijb = gpu_pkg.track_batch([path, path], start=start, stop=stop, target_width=25, start_location=loc, fps=fps,
+                                 chunk_steps=7, decode_workers=2)
+    np.testing.assert_array_equal(ijb[:, 0], pos)
+    np.testing.assert_array_equal(ijb[:, 1], pos)
+
+
+def test_downscale_against_opencv_bilinear(gpu_pkg):
+    """`imresize!(dia.buffer, img)` (src/diagnose.jl:33) → pt_batch_downscale, pinned against an independent
+    implementation: cv2.resize(INTER_LINEAR) samples at the same pixel-centre aligned positions (it quantises the
+    weights to 11 bits, hence the 1-level tolerance)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(12)
+    for (H, W) in [(1080, 1920), (480, 640), (270, 480)]:
+        base = cv2.GaussianBlur(rng.integers(0, 256, (H, W)).astype(np.uint8), (0, 0), 3)
+        with gpu_pkg.TrackerBatch(1, (H, W), 25, (45, 45), True) as b:
+            b.set_frames([base])
+            got = b.downscale(360, 640)[0]
+        ref = cv2.resize(base, (640, 360), interpolation=cv2.INTER_LINEAR)
+        assert np.abs(got.astype(int) - ref.astype(int)).max() <= 1

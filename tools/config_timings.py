@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import pt_import
 pkg = pt_import.load()
+from tools import synth
 
 
 def timed(label, fn, reps=3):
@@ -19,8 +20,8 @@ def timed(label, fn, reps=3):
 
 def config_track(label, H, W, nfr, tw, darker, start_location, window_size=None):
     start = (H // 2, W // 2)
-    tra = pkg.spiral(0.8 * min(H, W) / 2, 3000, start, seed=0)[:nfr]          # the 3000-frame spiral of the configs
-    vid = pkg.SyntheticVideo(H, W, tra, tw, darker, fps=24.0)
+    tra = synth.spiral(0.8 * min(H, W) / 2, 3000, start, seed=0)[:nfr]          # the 3000-frame spiral of the configs
+    vid = synth.SyntheticVideo(H, W, tra, tw, darker, fps=24.0)
     frames = np.stack([vid.frame(k) for k in range(nfr)])
     av = pkg.ArrayVideo(frames, fps=24.0)
     dt, (ts, ij) = timed(label, lambda: pkg.track(av, stop=nfr / 24.0, target_width=tw, start_location=start_location,
@@ -53,9 +54,9 @@ config_track("config 4b: 4K, 60 frames, light target tw=100, default window", 21
 
 # config 5: segmented multi-file video, SAR = 2, non-zero start, fps resampling (serial chain and parallel chains)
 H5, Wd5, sar5, src_fps, fps5 = 1080, 1920, 2, 24.0, 12.0
-_, tra5 = pkg.build_trajectory(0.8 * 540, src_fps, (540, 960), seconds=12.0, seed=0)
-parts = pkg.my_partition(len(tra5), 3)
-segs = [pkg.ArrayVideo(np.stack([pkg.SyntheticVideo(H5, Wd5, tra5[a:b + 1], 25, True, fps=src_fps, sar=sar5).frame(k)
+_, tra5 = synth.build_trajectory(0.8 * 540, src_fps, (540, 960), seconds=12.0, seed=0)
+parts = synth.my_partition(len(tra5), 3)
+segs = [pkg.ArrayVideo(np.stack([synth.SyntheticVideo(H5, Wd5, tra5[a:b + 1], 25, True, fps=src_fps, sar=sar5).frame(k)
                                  for k in range(b - a + 1)]), fps=src_fps, sar=sar5) for a, b in parts]
 seg_start = [0.25, 0.0, 0.0]
 seg_stop = [(b - a + 1) / src_fps for a, b in parts]

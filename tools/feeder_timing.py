@@ -7,14 +7,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cv2, pt_import
 pkg = pt_import.load()
+from tools import synth
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 nfr = int(sys.argv[2]) if len(sys.argv) > 2 else 120
 H, W = 480, 640
 tmp = tempfile.mkdtemp()
 paths, tras = [], []
 for s in range(N):
-    tra = pkg.spiral(0.8 * 240, 3000, (240, 320), seed=s)[:nfr]
-    vid = pkg.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
+    tra = synth.spiral(0.8 * 240, 3000, (240, 320), seed=s)[:nfr]
+    vid = synth.SyntheticVideo(H, W, tra, 25, True, fps=24.0)
     path = os.path.join(tmp, f"v{s}.avi")
     wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 24.0, (W, H), isColor=True)
     for k in range(nfr):

@@ -1,13 +1,13 @@
 import os, sys
 import numpy as np
 sys.path.insert(0, "/root/repo")
-os.environ["PT_DISABLE_RECT45"] = "1"
 import torch, bench, pt_import
 pkg = pt_import.load()
 H, W = 1080, 1920
 f = np.full((H, W), 128, np.uint8); bench.render_frame_host(f, (700, 1234))
 n = 8
 b = pkg.TrackerBatch(n, (H, W), 25, (45, 45), True)
+b.set_option("rect45", 0)
 b.set_frames([f] * n); b.set_fill(128)
 ext = torch.cuda.ExternalStream(b.stream, device=torch.device("cuda", 0))
 b.rect_argmax_all(0, 0, H, W)

@@ -33,7 +33,7 @@ for n in ns:
         best = min(best, e0.elapsed_time(e1) / reps)
     t = best * 1e-3
     print(f"fullframe 1080x1920 x{n}: {best*1e3/n:.1f} us/frame  {n*H*W/t/1e9:.1f} GP/s  "
-          f"{n*alg['flops']/t/1e12:.1f} TFLOP/s alg  correct={ok}  env chunks={os.environ.get('PT_R45_CHUNKS')}")
+          f"{n*alg['flops']/t/1e12:.1f} TFLOP/s alg  correct={ok}")
     b.set_window((270, 480))
     g = np.tile([540, 960], (n, 1)).astype(np.int32)
     b.step(g)

@@ -5,8 +5,13 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# the product library carries no probes: load the -DPT_PROBES build of the same sources
+os.environ["PAWSOME_CUDA_LIB"] = os.path.join(ROOT, "pawsometracker.jl_b200", "libpawsome_cuda_probes.so")
 import torch, bench, pt_import
 pkg = pt_import.load()
+import ctypes as _C
+pkg.lib.pt_debug_window45_timing.restype = _C.c_int
+pkg.lib.pt_debug_window45_timing.argtypes = [_C.c_void_p]
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 n, H, W = bench.N_VIDEOS, bench.H, bench.W
 dev = torch.device("cuda", 0)
