@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """bench.py — measures BASELINE.json's metric: tracked frames/s on batched 1080p
 synthetic videos (config "256 independent synthetic 1080p videos tracked
-concurrently in batched launches"), one process per GPU, weak scaling (256
-videos per GPU, sharded by video, no collective on the data path).
+concurrently in batched launches"), one process per GPU, sharded by video, no
+collective on the data path.  Default: weak scaling (256 videos per GPU);
+`--scaling strong` = BASELINE configs[2] as written: 256 videos IN TOTAL,
+video_id mod world (32 per GPU at N = 8 → the lone-window cluster kernel).  The
+weak line also carries the strong numbers as the supplementary `strong` object.
 
 A "step" is one lock-step time step of the hot path over the whole batch: one
 `trckr(guess)` (DoG over the 45×45 window of the constant-padded frame +
@@ -189,6 +192,17 @@ class Ranks:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
 
+    def gather(self, x: float, device=None):
+        """x of every rank, in rank order (a list of floats)."""
+        if not self.dist:
+            return [float(x)]
+        import torch
+        dev = device if self.backend == "nccl" else "cpu"
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        out = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     def close(self):
         if self.dist:
             self.dist.destroy_process_group()
@@ -202,10 +216,26 @@ def shard_videos(total: int, world: int, rank: int):
 # ---------------------------------------------------------------------------
 # CPU baseline (the oracle port; the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------
-def cpu_baseline(seconds_budget=10.0, seed=0):
+def cpu_baseline(seconds_budget=10.0, seed=0, gpu_sample=None):
+    """The oracle port timed on the host cores; with gpu_sample = (frames (T, m, H, W) u8, start (m, 2), gpu_ij (T, m, 2),
+    gpu_resp (T, m)) it also re-computes that sample of the timed GPU chain with the oracle (dense f64, reference loop
+    order): positions must be equal, responses within 1e-5·|R|."""
     from oracle import Oracle, build
     build()
     orc = Oracle()
+    checked = None
+    if gpu_sample is not None:
+        fr, st, gij, gresp = gpu_sample
+        T_, m_ = fr.shape[:2]
+        g = np.ascontiguousarray(st, np.int32)
+        ok_pos, worst = True, 0.0
+        for t in range(T_):
+            out, resp, _ = orc.batch_step_dense([fr[t, v] for v in range(m_)], [128] * m_, TW, True, (WS, WS), g, nthreads=0)
+            ok_pos &= bool(np.array_equal(out, gij[t]))
+            worst = max(worst, float(np.max(np.abs(gresp[t] - resp) / np.abs(resp))))
+            g = out
+        checked = {"videos": int(m_), "steps": int(T_), "positions_equal": bool(ok_pos), "max_rel_resp_err": worst,
+                   "ok": bool(ok_pos and worst <= 1e-5)}
     cores = orc.max_threads()
     nv = min(N_VIDEOS, max(8, 4 * cores))
     pos = orbit_positions(nv, seed)
@@ -228,7 +258,7 @@ def cpu_baseline(seconds_budget=10.0, seed=0):
     return {"value": done / el, "unit": "frames/s", "cores": int(used), "kind": "port",
             "sample": f"{done} window steps ({nv} of the 256 videos x {done // nv} passes of one 1080p time step), "
                       f"dense Float64 FIR in the reference's loop order, {el:.1f} s",
-            "positions_correct": ok}
+            "positions_correct": ok, "gpu_chain_vs_oracle": checked}
 
 
 def run_reference(args):

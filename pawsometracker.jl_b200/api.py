@@ -16,7 +16,7 @@ from typing import NamedTuple, Sequence
 
 import numpy as np
 
-from .feeder import FrameFeeder
+from .feeder import FrameFeeder, PinnedArray
 from .tracker import Tracker, TrackerBatch, fix_window_size, guess_window_size
 
 DEFAULT_MAX_DURATION_SECONDS = 86399.999  # src/PawsomeTracker.jl:19
@@ -244,11 +244,49 @@ def get_start_ij_and_tracker(start_location, vid, img, target_width, window_size
     return trckr, ij
 
 
+CHUNK_FRAMES = 64        # frames per chained library call of track_one
+
+
+def _track_chunks(trckr, vid, n, indices):
+    """The frame loop of track_one without a diagnostics writer: frames are taken CHUNK_FRAMES at a time and each
+    chunk is ONE library call (Tracker.track_frames → pt_batch_track_host: the chain ij[k] = trckr(ij[k-1]) runs
+    inside the library; page-locked frames are read in place by one chained kernel launch).  A source that hands out
+    contiguous frames by reference (`frame_ref`: frames already in host memory) is tracked in place; any other
+    source decodes into a ring of page-locked frames — the `read!(vid, trckr.img.data)` target of :166, K deep — so
+    the kernels read the decoder's output without a staging copy."""
+    ring = None
+    H, W = trckr.sz
+    dtype = trckr.img.dtype
+    contiguous = (W * dtype.itemsize, dtype.itemsize)
+    try:
+        while not vid.eof() and len(indices) < n:
+            frames = []
+            while not vid.eof() and len(indices) + len(frames) < n and len(frames) < CHUNK_FRAMES:
+                f = vid.read_ref()
+                if f is None or f.shape != (H, W) or f.dtype != dtype or f.strides != contiguous:
+                    if ring is None:
+                        ring = PinnedArray((CHUNK_FRAMES, H, W), dtype)
+                    slot = ring.array[len(frames)]
+                    if f is not None:
+                        np.copyto(slot, f)
+                    else:
+                        vid.read(out=slot)                      # read!(vid, trckr.img.data) (:166)
+                    f = slot
+                frames.append(f)
+            ij, _ = trckr.track_frames(frames, indices[-1])     # (:167) for the whole chunk
+            indices.extend((int(a), int(b)) for a, b in ij)
+    finally:
+        if ring is not None:
+            ring.close()
+
+
 def track_one(file, start, stop, target_width, start_location, window_size, darker_target, fps, dia=None, device=0):
     """src/PawsomeTracker.jl:148-174 with the intended loop body (:162, :167):
     `while !eof(vid) && last_frame < n`, `indices[k] = trckr(indices[k-1])`."""
     t = stop - start
     n = int(round(fps * t))
+    if n < 1:
+        raise ValueError(f"no frame to track: round(fps * (stop - start)) = {n} (the reference fails on `read` here)")
     ts = np.linspace(start, stop, n)                            # range(start, stop, n) (:152)
     dia = dia if dia is not None else _Dont()
     vid = _Resampled(open_video(file), start, t, fps)
@@ -259,6 +297,8 @@ def track_one(file, start, stop, target_width, start_location, window_size, dark
     try:
         dia(trckr, ij)
         own = trckr.img                                         # the tracker's private buffer (trckr.img.data)
+        if isinstance(dia, _Dont):
+            _track_chunks(trckr, vid, n, indices)               # no per-frame side channel: chained chunks
         while not vid.eof() and len(indices) < n:
             f = vid.read_ref()                                  # a frame the source already holds in host memory:
             if f is not None and f.shape == trckr.sz and f.dtype == own.dtype:
@@ -383,6 +423,9 @@ class _Chain:
             if (first or self.count < self.n) and not self.vid.eof():      # read(vid) :159, loop condition :162
                 f = self.vid.read_ref()                                    # by reference when the source allows
                 return (f if f is not None else self.vid.read()), first
+            if first:
+                # a segment that yields no frame at all: the serial path fails in `read(vid)` (:159) — so does this one
+                raise EOFError(f"segment {self.segs[self.k][0]} has no frame in [{self.segs[self.k][2]}, {self.segs[self.k][3]})")
             self._open_next()
         return None
 
@@ -488,8 +531,11 @@ def track_batch(files: Sequence, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, 
     """Batched counterpart with no equivalent in the reference: `track` over
     many independent videos of identical geometry advanced in lock-step, one
     CTA group per (video, window) per launch.  Per-video results are identical
-    to calling `track` on each video.  start_location: None, one location, or
-    one per video.  The videos are decoded concurrently by `decode_workers` host threads into a ring of
+    to calling `track` on each video — up to the length of the SHORTEST video: the
+    batch advances in lock-step and stops when any video reaches its end (`while
+    !eof(vid) && last_frame < n`, :162, with eof = any video's eof); track longer
+    videos separately (or in a second batch) if their tails matter.  start_location:
+    None, one location, or one per video.  The videos are decoded concurrently by `decode_workers` host threads into a ring of
     page-locked step-chunks (feeder.FrameFeeder) that the kernels read without a staging copy."""
     nv = len(files)
     if window_size is None:
@@ -498,6 +544,8 @@ def track_batch(files: Sequence, *, start=0, stop=DEFAULT_MAX_DURATION_SECONDS, 
     locs = list(start_location) if isinstance(start_location, list) else [start_location] * nv
     t = stop - start
     n = int(round(fps * t))
+    if n < 1:
+        raise ValueError(f"no frame to track: round(fps * (stop - start)) = {n}")
     ts = np.linspace(start, stop, n)
     vids = [_Resampled(open_video(f), start, t, fps) for f in files]
     first = [v.read() for v in vids]

@@ -585,7 +585,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     CU(cudaSetDevice(device));
     int smem_optin = 0;      // (cudaGetDeviceProperties costs ~20 ms per call; one attribute is microseconds)
     CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    if (pt::generic_smem_bytes(L, Lpad) > (size_t)smem_optin)
+    if (pt::generic_smem_bytes(L, Lpad) + 256 > (size_t)smem_optin)      // (+ the kernel's static shared memory)
         return fail(PT_ERR_UNSUPPORTED, "kernel length %d (target_width %g) needs %zu B shared memory, device allows %zu",
                     L, tw, pt::generic_smem_bytes(L, Lpad), (size_t)smem_optin);
 

@@ -362,9 +362,15 @@ cudaError_t generic_init_device()
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dog_rect_argmax_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    // the opt-in limit covers static + dynamic shared memory: leave room for the kernel's few static bytes
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, dog_rect_argmax_generic<uint8_t>);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(dog_rect_argmax_generic<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute(dog_rect_argmax_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&fa, dog_rect_argmax_generic<float>);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(dog_rect_argmax_generic<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
 }
 
 cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s)

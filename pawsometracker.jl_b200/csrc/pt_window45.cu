@@ -134,7 +134,9 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 // conversion so a frame that is cold in L2/HBM costs one memory round trip.
 // NROWS = rows staged into s_in rows 0..NROWS-1 (109 for a whole footprint, 45 for the next batch of a marching strip).
 // f32 frames: lane = column (+32q), coalesced 4-byte loads.
-template <int NROWS, int FCOLS = FC, int PITCH = PIN>
+// kContig: warp w takes the contiguous rows [w·RPW, (w+1)·RPW) instead of w, w+8, … (the cluster kernel row-filters
+// the rows a warp staged without a CTA barrier in between).
+template <int NROWS, int FCOLS = FC, int PITCH = PIN, bool kContig = false>
 __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H, int W, int fy0, int fx0,
                                            float fill, float *s_in, int warp, int lane)
 {
@@ -143,7 +145,7 @@ __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H,
     float px[RPW][NQ];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        const int f = warp + r * NWARPS;
+        const int f = kContig ? warp * RPW + r : warp + r * NWARPS;
         const int Y = fy0 + f;
         const bool yok = (f < NROWS) && (Y >= 0) && (Y < H);
         const float *rowp = frame + (size_t)(yok ? Y : 0) * pitch;
@@ -156,7 +158,7 @@ __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H,
     }
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        const int f = warp + r * NWARPS;
+        const int f = kContig ? warp * RPW + r : warp + r * NWARPS;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int c = lane + 32 * q;
@@ -172,7 +174,7 @@ __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H,
 // exact.  Each lane rotates its word by lane/8 bytes so the four stores of a warp hit 32
 // distinct banks.  Requires frame base, pitch and strides to be multiples of 4 bytes and
 // pitch ≥ round_up(W, 4) (checked by window45_supported).
-template <int NROWS, bool kInterior, int FCOLS = FC, int PITCH = PIN>
+template <int NROWS, bool kInterior, int FCOLS = FC, int PITCH = PIN, bool kContig = false>
 __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
                                               float fill, float *s_in, int warp, int lane)
 {
@@ -198,12 +200,12 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
     unsigned int wd[RPW];
     // one running row pointer (bumped by NWARPS rows per load): two integer instructions per load instead of a
     // fresh 64-bit row-times-pitch product
-    const uint8_t *rowp = frame + ((long long)(fy0 + warp) * pitch + X);   // only dereferenced when valid
-    const unsigned long long rstep = (unsigned long long)(NWARPS * pitch);
+    const uint8_t *rowp = frame + ((long long)(fy0 + (kContig ? warp * RPW : warp)) * pitch + X);   // only dereferenced when valid
+    const unsigned long long rstep = (unsigned long long)((kContig ? 1 : NWARPS) * pitch);
     unsigned long long addr = reinterpret_cast<unsigned long long>(rowp);
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        const int f = warp + r * NWARPS;
+        const int f = kContig ? warp * RPW + r : warp + r * NWARPS;
         const int Y = fy0 + f;
         const bool ok = wordok && (f < NROWS) && (kInterior || ((Y >= 0) && (Y < H)));
         wd[r] = fillw;
@@ -214,7 +216,7 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
     const unsigned int magic = 0x4B000000u;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        const int f = warp + r * NWARPS;
+        const int f = kContig ? warp * RPW + r : warp + r * NWARPS;
         if (f < NROWS) {
             unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
             w = __funnelshift_r(w, w, 8 * rot);            // byte k of w = pixel (k + rot) & 3 of the word
@@ -228,15 +230,15 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
     }
 }
 
-template <int NROWS, int FCOLS = FC, int PITCH = PIN>
+template <int NROWS, int FCOLS = FC, int PITCH = PIN, bool kContig = false>
 __device__ __forceinline__ void stage_rows(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
                                            float fill, float *s_in, int warp, int lane)
 {
     // interior: every aligned word the rows touch lies inside the frame → no byte masks, no row checks
     constexpr int NWORDS = (FCOLS + 3 + 3) / 4;               // aligned words covering FCOLS columns at any phase (28 for 109)
     const bool interior = (fy0 >= 0) && (fy0 + NROWS <= H) && ((fx0 & ~3) >= 0) && ((fx0 & ~3) + 4 * NWORDS <= W);
-    if (interior) stage_rows_u8<NROWS, true, FCOLS, PITCH>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
-    else stage_rows_u8<NROWS, false, FCOLS, PITCH>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    if (interior) stage_rows_u8<NROWS, true, FCOLS, PITCH, kContig>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    else stage_rows_u8<NROWS, false, FCOLS, PITCH, kContig>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
 }
 
 template <typename PixT>
@@ -803,18 +805,27 @@ dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
 // the guess was outside the frame and got clamped) re-fetches its own region.  Other frames (f32, unaligned)
 // are staged straight from global memory with the L2 prefetch of dog_window45_argmax.
 //
-// Layouts: s_in [109][PINS] f32, PINS odd (lanes walk rows); s_midT [slice column][109] float2 — the column pass
-// walks rows of one column, items ordered row-group-fastest: consecutive items are 5·(item) float2 apart
-// (mod 16 bank pairs), i.e. conflict-free for any 16 consecutive lanes.
+// Per step a CTA runs: [stage own 14 rows → row pass of those rows] per warp, independently (no CTA barrier in
+// between: a warp's load latency hides behind the other warps' FMAs) → one CTA barrier → column pass → candidates to
+// every CTA of the cluster with st.async + mbarrier (no cluster-wide rendezvous; the wait doubles as the CTA's
+// second barrier) → fold, next guess.
+//
+// Layouts: s_in [109][PINS] f32 with PINS chosen so that the (row, group) lanes of a row-pass warp hit distinct
+// banks; s_midT [slice column][109] float2 — the column pass walks rows of one column, items ordered
+// row-group-fastest: consecutive items are RC·(item) float2 apart (mod 16 bank pairs), i.e. conflict-free for
+// any 16 consecutive lanes.
 // ---------------------------------------------------------------------------------------------------
 template <int C>
 struct SliceGeom {
     static constexpr int SW = (WC + C - 1) / C;              // widest slice: 23 / 12 / 6 columns
-    static constexpr int RRS = 6;                            // row pass: outputs per thread
-    static constexpr int NGR = (SW + RRS - 1) / RRS;         // groups per row: 4 / 2 / 1
+    static constexpr int RRS = (C == 8) ? 3 : 6;             // row pass: outputs per thread
+    static constexpr int NGR = (SW + RRS - 1) / RRS;         // groups per row: 4 / 2 / 2
     static constexpr int SWC = NGR * RRS;                    // computed columns (≥ SW; the surplus is masked)
     static constexpr int SFC = SWC + 2 * HW;                 // staged footprint columns: 88 / 76 / 70
-    static constexpr int PINS = SFC | 1;                     // odd pitch
+    static constexpr int RPW = (FR + NWARPS - 1) / NWARPS;   // 14 consecutive footprint rows per warp (stage AND row pass)
+    // s_in pitch: the lanes of a row-pass warp are (row r < 14, group g) at r·PINS + g·RRS — these pitches make the
+    // 28 (C = 4, 8) / 32-at-a-time (C = 2) addresses fall into distinct banks
+    static constexpr int PINS = (C == 2) ? 101 : (C == 4) ? 85 : 70;
     static constexpr int NW = (SFC + 3 + 3) / 4;             // aligned words per staged row at any phase
     static constexpr int RC = (C == 8) ? 3 : 5;              // column pass: outputs per thread
     static constexpr int NGC = WR / RC;                      // row groups: 9 / 15
@@ -882,22 +893,30 @@ __device__ __forceinline__ unsigned int cluster_rank()
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void st_cluster_u64(unsigned int local_addr, unsigned int rank, unsigned long long v)
+__device__ __forceinline__ unsigned int mapa_u32(unsigned int local_addr, unsigned int rank)
 {
     unsigned int remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
+    return remote;
+}
+// 8-byte store into the shared memory of CTA `rank` of the cluster that completes 8 bytes on that CTA's mbarrier:
+// the receiver only waits on its own mbarrier, no cluster-wide rendezvous.
+__device__ __forceinline__ void st_async_u64(unsigned int local_addr, unsigned int local_mbar, unsigned int rank, unsigned long long v)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(mapa_u32(local_addr, rank)), "l"(v), "r"(mapa_u32(local_mbar, rank)) : "memory");
 }
 
-// u8 → f32 conversion of one footprint slice out of the prefetched u8 region in shared memory: the same word /
-// PRMT / 2^23 scheme as stage_rows_u8, LDS instead of LDG.  rgn row 0 ↔ frame row rgn_y0, rgn byte 0 ↔ frame
-// column rgn_xa (multiple of 16).  Bytes outside the frame were never copied: they are replaced by the fill byte.
+// u8 → f32 conversion of the footprint rows of one warp (rows [warp·14, warp·14 + 14)) out of the prefetched u8 region
+// in shared memory: the same word / PRMT / 2^23 scheme as stage_rows_u8, LDS instead of LDG.  rgn row 0 ↔ frame row
+// rgn_y0, rgn byte 0 ↔ frame column rgn_xa (multiple of 16).  Bytes outside the frame were never copied: they are
+// replaced by the fill byte.  (Flattening the (row, word) pairs over all lanes was measured: no gain, more registers.)
 template <int C, bool kInterior>
 __device__ __forceinline__ void convert_slice_u8(const uint8_t *rgn, int rgn_y0, int rgn_xa, int H, int W, int fy0, int fxs,
                                                  float fill, float *s_in, int warp, int lane)
 {
     using G = SliceGeom<C>;
-    constexpr int RPW = (FR + NWARPS - 1) / NWARPS;
+    constexpr int RPW = G::RPW;
     const int xw0 = fxs & ~3, phase = fxs - xw0;
     const int X = xw0 + 4 * lane;
     const unsigned int fillw = (unsigned int)fill * 0x01010101u;
@@ -917,20 +936,21 @@ __device__ __forceinline__ void convert_slice_u8(const uint8_t *rgn, int rgn_y0,
         cok[k] = col[k] >= 0 && col[k] < G::SFC;
     }
     unsigned int wd[RPW];
-    const uint8_t *src = rgn + (fy0 + warp - rgn_y0) * G::SPAN + (X - rgn_xa);
+    const int f0 = warp * RPW;
+    const uint8_t *src = rgn + (fy0 + f0 - rgn_y0) * G::SPAN + (X - rgn_xa);
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        const int f = warp + r * NWARPS;
+        const int f = f0 + r;
         const int Y = fy0 + f;
         const bool ok = wordok && (f < FR) && (kInterior || ((Y >= 0) && (Y < H)));
         wd[r] = fillw;
-        if (ok) wd[r] = *reinterpret_cast<const unsigned int *>(src + r * (NWARPS * G::SPAN));
+        if (ok) wd[r] = *reinterpret_cast<const unsigned int *>(src + r * G::SPAN);
     }
     const float cst = 8388608.0f + fill;
     const unsigned int magic = 0x4B000000u;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        const int f = warp + r * NWARPS;
+        const int f = f0 + r;
         if (f < FR) {
             unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
             w = __funnelshift_r(w, w, 8 * rot);
@@ -944,16 +964,21 @@ __device__ __forceinline__ void convert_slice_u8(const uint8_t *rgn, int rgn_y0,
     }
 }
 
-// Row pass of a slice: item = (footprint row f, group g of 6 output columns), lanes walk rows; same folded
-// arithmetic (and summation order) as row_pass45.  Output → s_midT[column][row].
+// Row pass of a slice over the 14 rows THIS WARP staged (no CTA barrier between staging and row pass: warps run
+// through both independently, one warp's load latency hides behind another's FMAs): item = (row r of the warp, group g
+// of RRS output columns), same folded arithmetic and summation order as row_pass45.  Output → s_midT[column][row].
 template <int C>
-__device__ __forceinline__ void row_pass_slice(const float *s_in, float2 *s_midT, int tid, const Taps45 &tp)
+__device__ __forceinline__ void row_pass_slice(const float *s_in, float2 *s_midT, int warp, int lane, const Taps45 &tp)
 {
     using G = SliceGeom<C>;
-    constexpr int RRS = G::RRS;
+    constexpr int RRS = G::RRS, RPW = G::RPW;
+    const int f0 = warp * RPW;
+    const int nrows = min(RPW, FR - f0);                     // 14 (11 for the last warp)
 #pragma unroll 1
-    for (int item = tid; item < FR * G::NGR; item += CL_THREADS) {
-        const int g = item / FR, f = item - g * FR;
+    for (int item = lane; item < RPW * G::NGR; item += 32) {
+        const int g = item / RPW, r = item - g * RPW;
+        if (r >= nrows) continue;
+        const int f = f0 + r;
         const float *row = s_in + f * G::PINS + g * RRS;
         float x[RRS + 2 * HW];
 #pragma unroll
@@ -973,6 +998,15 @@ __device__ __forceinline__ void row_pass_slice(const float *s_in, float2 *s_midT
 #pragma unroll
         for (int j = 0; j < RRS; ++j) dst[j * FR] = acc[j];
     }
+}
+
+// max over the warp of 64-bit keys with two 32-bit REDUX (instead of five rounds of 64-bit shuffles)
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long key)
+{
+    const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
+    const unsigned int mh = __reduce_max_sync(0xFFFFFFFFu, hi);
+    const unsigned int ml = __reduce_max_sync(0xFFFFFFFFu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | (unsigned long long)ml;
 }
 
 // Column pass of a slice + per-thread argmax: item = (slice column x, group h of RC output rows), h fastest.
@@ -1034,7 +1068,8 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
 {
     using G = SliceGeom<C>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_mbar[2];
+    __shared__ __align__(8) unsigned long long s_mbar[2];                // arrival of the prefetched regions
+    __shared__ __align__(8) unsigned long long s_xbar[2];                // arrival of the argmax candidates (by step parity)
     __shared__ __align__(8) unsigned long long s_xk[2][NWARPS * C];      // candidates of every warp of every CTA of the cluster
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1047,11 +1082,14 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
     float *s_in = reinterpret_cast<float *>(smem_raw + (bulk ? 2 * G::RGN_BYTES + 128 : 0));
     float2 *s_midT = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(s_in) + G::IN_BYTES);
     const unsigned int mbar0 = smem_u32(&s_mbar[0]);
+    const unsigned int xbar0 = smem_u32(&s_xbar[0]);
     const unsigned int rgn0 = smem_u32(rgn);
 
     if (tid == 0) {
         mbar_init(mbar0, 1u);
         mbar_init(mbar0 + 8u, 1u);
+        mbar_init(xbar0, 1u);
+        mbar_init(xbar0 + 8u, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1062,7 +1100,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
     int2 g = a.guess[v];
     const PixT *frame0 = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
     int rgn_y0[2] = {0, 0}, rgn_xa[2] = {0, 0};
-    unsigned int ph[2] = {0u, 0u};
+    unsigned int ph[2] = {0u, 0u}, xph[2] = {0u, 0u};
 
     // request the region around footprint origin (cfy0, cfxs) of step `ts` (frame `frame`) into buffer `buf`:
     // use_bulk 2 → one TMA tile copy, use_bulk 1 → one bulk copy per row
@@ -1098,6 +1136,8 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
     for (int t = 0; t < a.T; ++t) {
         const int par = t & 1;
         PT_PROBE_BEGIN(a, v, t, tid + rank)
+        // this step's candidates: 8 bytes from every warp of every CTA of the cluster (this CTA's own included)
+        if (tid == 0) mbar_arrive_expect_tx(xbar0 + 8u * par, 8u * NWARPS * C);
         const PixT *frame = frame0 + (size_t)t * a.step_stride;
         const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);
         const int fy0 = wy0 - HW, fxs = wx0 - HW + xs;                       // footprint origin of this slice
@@ -1118,7 +1158,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
             // everything the next step can touch → the other buffer (last read by the previous step's conversion)
             if (t + 1 < a.T) issue_region(par ^ 1, frame + a.step_stride, t + 1, fy0, fxs);
         } else {
-            stage_rows<FR, G::SFC, G::PINS>(frame, a.pitch, a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
+            stage_rows<FR, G::SFC, G::PINS, true>(frame, a.pitch, a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
             if (t + 1 < a.T) {                                               // warm L2 with the next step's region
                 const PixT *nframe = frame + a.step_stride;
                 constexpr int NLMAX = (int)(((G::SFC + WC) * sizeof(PixT) + 127) / 128) + 1;
@@ -1137,34 +1177,27 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();                        // a warp row-filters exactly the rows it staged: no CTA barrier here
         PT_PROBE(2, tid + rank);
 
-        row_pass_slice<C>(s_in, s_midT, tid, tp);
-        __syncthreads();
+        row_pass_slice<C>(s_in, s_midT, warp, lane, tp);
+        __syncthreads();                     // the column pass reads every warp's rows of s_midT
         PT_PROBE(3, tid + rank);
 
-        unsigned long long key = col_pass_slice<C>(s_midT, tid, tp, width, 0, xs, WR, WC);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
-            key = o > key ? o : key;
-        }
-        // every warp hands its candidate to every CTA of the cluster (its own included), slots double-buffered by
-        // step parity: a CTA can only overwrite slot `par` two steps later, i.e. after the next cluster barrier,
-        // which every CTA reaches only after it has read this step's slots
-        if (lane < C) st_cluster_u64(smem_u32(&s_xk[par][rank * NWARPS + warp]), (unsigned int)lane, key);
-        cluster_arrive();
-        cluster_wait();
+        unsigned long long key = warp_max_key(col_pass_slice<C>(s_midT, tid, tp, width, 0, xs, WR, WC));
+        // Every warp hands its candidate to every CTA of the cluster (its own included) with st.async, which also
+        // completes 8 bytes on the receiver's mbarrier; a CTA waits only for ITS 8·C·8 bytes — no cluster-wide
+        // rendezvous.  Slots and mbarriers are double-buffered by step parity: a CTA can only send step t+2 after it
+        // received every CTA's step t+1 candidates, which each of them sends only after it has read step t's slots.
+        if (lane < C) st_async_u64(smem_u32(&s_xk[par][rank * NWARPS + warp]), xbar0 + 8u * par, (unsigned int)lane, key);
+        // (this wait is also the CTA's barrier between this step's column pass and the next step's row pass: all eight
+        // warps of this CTA have sent their candidates, i.e. finished reading s_midT, before it completes)
+        mbar_wait(xbar0 + 8u * par, xph[par]); xph[par] ^= 1u;
         PT_PROBE(4, tid + rank);
         {
             unsigned long long k = s_xk[par][lane % (NWARPS * C)];
             if (NWARPS * C > 32) { const unsigned long long k2 = s_xk[par][32 + lane]; k = k2 > k ? k2 : k; }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, k, off);
-                k = o > k ? o : k;
-            }
+            k = warp_max_key(k);
             const unsigned int idx = key_index(k);
             const int xx = (int)(idx / WR), yy = (int)(idx - xx * WR);
             const int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;                   // absolute index (:60)
@@ -1182,7 +1215,11 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
             g = make_int2(ci, cj);
         }
     }
-    // (the last cluster barrier above already ordered every remote store before any CTA can exit)
+    // A CTA may only exit when no peer can still write into its shared memory: it has received all candidates of the
+    // last step by then, and every earlier store was received before that.  Its own outgoing stores target CTAs that
+    // are still waiting for them.  One closing barrier keeps the cluster's lifetime simple and costs once per launch.
+    cluster_arrive();
+    cluster_wait();
 }
 
 // How many CTAs share one window for this launch (1 = the per-SM kernels above).
@@ -1244,8 +1281,7 @@ static cudaError_t launch_cluster_t(Args45 k, const Taps45 &tp, int use_bulk, cu
         }
         if (!ok) use_bulk = 1;
     }
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof lc);
+    cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(k.n * C));
     lc.blockDim = dim3(CL_THREADS);
     lc.dynamicSmemBytes = SliceGeom<C>::smem_bytes(use_bulk != 0);

@@ -306,6 +306,25 @@ class Tracker:
         self.last_response = float(resp[0])
         return (out[0], out[1])
 
+    def track_frames(self, frames, guess):
+        """The frame loop `indices[k] = trckr(indices[k-1])` (src/PawsomeTracker.jl:163-169) over a list of host frames
+        in ONE library call (pt_batch_track_host): frames in page-locked memory (pt_host_alloc / PinnedArray — where a
+        decoder should write them) are read in place by one chained launch; pageable frames take the per-step
+        footprint path inside the library.  Returns (ij (T, 2) int32, resp (T,) float32)."""
+        T = len(frames)
+        pitches = {_check_frame(f, self.sz[0], self.sz[1], self._batch.pixel) for f in frames}
+        if len(pitches) != 1:
+            raise ValueError("all frames of a chunk must share one pitch")
+        ptrs = (C.c_void_p * T)(*[f.ctypes.data for f in frames])
+        g = (C.c_int32 * 2)(int(guess[0]), int(guess[1]))
+        out = np.empty((T, 2), np.int32)
+        resp = np.empty(T, np.float32)
+        h = self._batch._h
+        check(lib.pt_batch_set_guess(h, g))
+        check(lib.pt_batch_track_host(h, ptrs, T, pitches.pop(), 0, out.ctypes.data_as(_i32p), resp.ctypes.data_as(_fp)))
+        self.last_response = float(resp[-1])
+        return out, resp
+
     def step_resident(self, guess):
         """Same result with the whole frame uploaded to HBM first (the
         `read!` + step of the reference's loop, :166-167)."""

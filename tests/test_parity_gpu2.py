@@ -20,6 +20,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
+# Response tolerance of the exact-tie tests.  A texture whose period is below the 45-px window lies far outside the
+# pass band of the DoG (σ = 10.6 px): max|R| is only 1e-4 … 1e-3 of the pixel contrast, so the FP32 rounding floor
+# (≈ 1e-8 absolute for pixels in [0, 1], the same floor as everywhere else) is no longer small against max|R|.  The
+# tie DECISION is what these tests pin; the response is held to RTOL·max|R| or this absolute floor.
+ABS_FLOOR = 1e-7
 
 
 def disk_frame(H, W, cy, cx, r, val=0, bg=128):
@@ -175,7 +180,8 @@ def _check_exact_tie(trk, oracle, f, tw, darker, ws, guess, dense, min_ties):
     assert (gi, gj) == (oi, oj)
     assert got == (ref.i, ref.j)
     assert resp == rmap[gi, gj]
-    assert abs(resp - ref.resp) <= RTOL * ref.maxabs
+    assert abs(resp - ref.resp) <= max(RTOL * ref.maxabs, ABS_FLOOR)
+    assert np.abs(rmap.astype(np.float64) - ref.R).max() <= max(RTOL * ref.maxabs, ABS_FLOOR)
     return got
 
 
@@ -260,7 +266,7 @@ def test_exact_ties_in_a_batch_through_rot_and_static(gpu_pkg, oracle):
             r = oracle.step(frames[t, v], int(fills[v]), 25, True, (45, 45), g, dense=True)
             assert r.resp == r.second                      # an exact tie at every step
             assert tuple(ij_st[t, v]) == (r.i, r.j), (v, t)
-            assert abs(r_st[t, v] - r.resp) <= RTOL * r.maxabs
+            assert abs(r_st[t, v] - r.resp) <= max(RTOL * r.maxabs, ABS_FLOOR)
             g = (r.i, r.j)
 
 

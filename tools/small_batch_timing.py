@@ -40,11 +40,14 @@ for n in ns:
             ts = []
             for _ in range(7):
                 benchlib.flush_l2(flush.data_ptr(), flush.numel(), b.stream)
-                b.set_guess(pos[0]); torch.cuda.synchronize()
+                # 3 untimed warm-up steps (they also upload the guess), then T timed steps — bench.py's protocol
+                b.set_guess(pos[(Tmax - 3) % bench.PERIOD]); b.track_device_async(ring.data_ptr() + (Tmax - 3) * n * H * W, n * H * W, H * W, W, 3)
+                b.set_guess(pos[0]); b.track_device_async(ring.data_ptr(), n * H * W, H * W, W, 1)
+                torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 with torch.cuda.stream(ext):
-                    e0.record(); b.track_device_async(ring.data_ptr(), n * H * W, H * W, W, T); e1.record()
-                torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+                    e0.record(); b.track_device_async(ring.data_ptr() + n * H * W, n * H * W, H * W, W, T - 1); e1.record()
+                torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) * T / (T - 1))
             t = float(np.median(ts))
             row.append(f"T={T}: {t*1e3/T:6.2f} us/step ({n*T/t/1e3:7.2f} M frames/s){'' if ok else ' WRONG'}")
         print(f"n={n:3d} {name:12s} {b.last_kernel:24s} " + "   ".join(row), flush=True)
