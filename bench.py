@@ -155,6 +155,46 @@ class ClockSampler:
                 "samples": len(mhz), "power_w_max": max(watts) if watts else None}
 
 
+def measure_pcie_rx(dev_index, call, reset, steps_per_call, seconds=0.4):
+    """PCIe RX bytes per step of `call` (which advances `steps_per_call` steps), from NVML's RX throughput counter
+    sampled (20 ms windows) in a thread while `call` runs back to back.  None when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev_index)
+        pynvml.nvmlDeviceGetPcieThroughput(h, pynvml.NVML_PCIE_UTIL_RX_BYTES)
+    except Exception as e:      # noqa: BLE001
+        return {"available": False, "why": repr(e)[:120]}
+    samples, stop = [], threading.Event()
+
+    def sampler():
+        while not stop.is_set():
+            try:
+                samples.append(pynvml.nvmlDeviceGetPcieThroughput(h, pynvml.NVML_PCIE_UTIL_RX_BYTES))   # KB/s
+            except Exception:   # noqa: BLE001
+                break
+
+    th = threading.Thread(target=sampler, daemon=True)
+    calls, t0 = 0, time.perf_counter()
+    th.start()
+    while time.perf_counter() - t0 < seconds:
+        reset()
+        call()
+        calls += 1
+    el = time.perf_counter() - t0
+    stop.set()
+    th.join(timeout=1.0)
+    if not samples or calls == 0:
+        return {"available": False, "why": "no samples"}
+    inner = samples[1:-1] if len(samples) > 3 else samples         # the first / last windows straddle the loop edges
+    rx = float(np.mean(inner)) * 1e3                                # bytes/s
+    steps_per_s = calls * steps_per_call / el
+    return {"available": True, "rx_gb_per_s": rx / 1e9, "bytes_per_step": rx / steps_per_s, "samples": len(samples),
+            "steps_per_s_during_measurement": steps_per_s,
+            "note": "nvmlDeviceGetPcieThroughput(RX) averaged over 20 ms windows while pt_batch_track_host (zero-copy "
+                    "footprint streaming) ran back to back; includes the pointer-table upload and result stores' acks"}
+
+
 # ---------------------------------------------------------------------------
 # distributed plumbing (no data-path collective: barrier + max-over-ranks only)
 # ---------------------------------------------------------------------------
@@ -292,8 +332,8 @@ def run_reference(args):
               f"FIR in the reference's loop order, {used} host threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.scaling, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": int(used), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "positions_correct": all(orc_steps),
@@ -302,7 +342,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config():
+def workload_config(scaling="weak", world=1):
+    if scaling == "strong":
+        return {"workload": f"BASELINE configs[2] as written: {N_VIDEOS} independent synthetic 1080p videos IN TOTAL, "
+                            "sharded video_id mod world, dark disk target_width=25 (l=65), default 45x45 window, one "
+                            "batched launch per time step",
+                "videos_total": N_VIDEOS, "videos_per_gpu": len(shard_videos(N_VIDEOS, world, 0)), "frame": [H, W],
+                "target_width": TW, "window": WS, "pixel": "u8 (Gray{N0f8}) frames in HBM, FP32 arithmetic",
+                "sharding": "whole videos per rank (video_id mod world), no collective"}
     return {"workload": "BASELINE configs[2]: 256 independent synthetic 1080p videos per GPU, dark disk "
                         "target_width=25 (l=65), default 45x45 window, one batched launch per time step",
             "videos_per_gpu": N_VIDEOS, "frame": [H, W], "target_width": TW, "window": WS,
@@ -326,7 +373,9 @@ def run_gpu(args, ranks):
     torch.cuda.set_device(dev_index)
     device = torch.device("cuda", dev_index)
     K, Wm = args.steps, args.warmup
-    n = N_VIDEOS
+    strong = args.scaling == "strong"
+    # weak: 256 videos per GPU; strong: 256 videos in total, video_id mod world (BASELINE configs[2] as written)
+    n = len(shard_videos(N_VIDEOS, ranks.world, ranks.rank)) if strong else N_VIDEOS
     seed = 1000 * ranks.rank
 
     # ---- resident workload: ring of step-slots in HBM, never re-read inside a timed region
@@ -352,8 +401,11 @@ def run_gpu(args, ranks):
 
     # correctness of exactly what is timed: W+K chained steps from slot 0
     batch.set_guess(pos[0])
-    ij_chk, _ = batch.track_device(ring.data_ptr(), step_stride, frame_stride, W, min(Wm + K, slots))
+    ij_chk, resp_chk = batch.track_device(ring.data_ptr(), step_stride, frame_stride, W, min(Wm + K, slots))
     resident_ok = bool(np.array_equal(ij_chk, truth_for_steps(pos, min(Wm + K, slots))))
+    # a sample of exactly this chain for the oracle (checked on rank 0 inside the cpu_baseline leg)
+    Ts, ms_ = min(Wm + K, slots, 24), min(n, 8)
+    gpu_sample = (ring[:Ts, :ms_].cpu().numpy(), pos[0][:ms_].copy(), ij_chk[:Ts, :ms_].copy(), resp_chk[:Ts, :ms_].copy())
 
     sampler = ClockSampler(dev_index, period_ms=20)
     sampler.__enter__()
@@ -367,7 +419,7 @@ def run_gpu(args, ranks):
 
     launches_before = batch.launch_count
     batch_kernel = batch.kernel_name
-    reps_ms = []
+    reps_ms, reps_local = [], []
     t_wall0 = time.perf_counter()
     if True:
         rep = 0
@@ -387,7 +439,8 @@ def run_gpu(args, ranks):
             batch_kernel = batch.last_kernel or batch_kernel
             torch.cuda.synchronize(device)
             ranks.barrier()
-            reps_ms.append(ranks.max_over_ranks(e0.elapsed_time(e1), device))        # max over ranks, device time
+            reps_local.append(e0.elapsed_time(e1))
+            reps_ms.append(ranks.max_over_ranks(reps_local[-1], device))             # max over ranks, device time
             rep += 1
             if rep >= args.repeats or (rep >= 5 and time.perf_counter() - t_wall0 > 2.5):
                 break
@@ -396,7 +449,57 @@ def run_gpu(args, ranks):
     del launches_before
     ms_K = float(np.median(reps_ms))
     world = ranks.world
-    value = world * n * K / (ms_K * 1e-3)
+    n_all = int(round(ranks.sum_over_ranks(float(n), device)))       # videos of all ranks (256·world weak, 256 strong)
+    value = n_all * K / (ms_K * 1e-3)
+    ms_K_per_rank = ranks.gather(float(np.median(reps_local)), device)
+
+    # ---- supplementary: BASELINE configs[2] as written (256 videos IN TOTAL, video_id mod world) measured in the same
+    # weak-scaling run: this rank tracks 256/world of its videos with the same protocol.  With few windows per GPU the
+    # library switches to the lone-window cluster kernel (2, 4 or 8 CTAs per window).
+    strong_obj = None
+    if not strong and world > 1 and not args.no_strong:
+        ns = len(shard_videos(N_VIDEOS, world, ranks.rank))
+        bs = pkg.TrackerBatch(ns, (H, W), TW, (WS, WS), True, dtype=np.uint8, device=dev_index)
+        bs.bind_device_frames(ring.data_ptr(), H * W, W)
+        bs.set_fill([128] * ns)
+        exts = torch.cuda.ExternalStream(bs.stream, device=device)
+
+        def chain_s(first_slot, nsteps):
+            done = 0
+            while done < nsteps:
+                sl = (first_slot + done) % slots
+                m2 = min(nsteps - done, slots - sl)
+                bs.track_device_async(ring.data_ptr() + sl * step_stride, step_stride, frame_stride, W, m2)
+                done += m2
+
+        bs.set_guess(pos[0][:ns])
+        chk_s, _ = bs.track_device(ring.data_ptr(), step_stride, frame_stride, W, min(Wm + K, slots))
+        ok_s = bool(np.array_equal(chk_s, truth_for_steps(pos, min(Wm + K, slots))[:, :ns]))
+        ms_s, loc_s = [], []
+        for _ in range(12):
+            benchlib.flush_l2(flush.data_ptr(), flush.numel(), bs.stream)
+            bs.set_guess(pos[0][:ns])
+            chain_s(0, Wm)
+            ranks.barrier()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(exts):
+                e0.record()
+                chain_s(Wm % slots, K)
+                e1.record()
+            torch.cuda.synchronize(device)
+            ranks.barrier()
+            loc_s.append(e0.elapsed_time(e1))
+            ms_s.append(ranks.max_over_ranks(loc_s[-1], device))
+        kern_s = bs.last_kernel
+        bs.close()
+        t_s = float(np.median(ms_s)) * 1e-3
+        ok_s_all = ranks.sum_over_ranks(0.0 if ok_s else 1.0, device) == 0.0
+        strong_obj = {"scaling": "strong", "videos_total": N_VIDEOS, "videos_per_gpu": ns, "value": N_VIDEOS * K / t_s,
+                      "unit": "frames/s", "us_per_step": t_s / K * 1e6, "kernel": kern_s, "positions_correct": bool(ok_s_all),
+                      "ms_K_per_rank": ranks.gather(float(np.median(loc_s)), device),
+                      "note": "supplementary: BASELINE configs[2] as written (256 videos in total sharded over the GPUs), "
+                              "same timing protocol as `value`, max over ranks"}
 
     # ---- mode(frame) = fill value of each video's first frame (src/PawsomeTracker.jl:47): one HBM pass
     benchlib.flush_l2(flush.data_ptr(), flush.numel(), batch.stream)
@@ -596,15 +699,21 @@ def run_gpu(args, ranks):
         dt = time.perf_counter() - t0
         ranks.barrier()
         ok = bool(np.array_equal(ij, truth_for_steps(pos_h, nsteps_k, first=nsteps_w)))
-        return ranks.max_over_ranks(dt, device), ok
+        return ranks.max_over_ranks(dt, device), ok, dt
 
     lb = batch.launch_count
-    dt_fp, ok_fp = min((e2e_run("footprint", Wm, K) for _ in range(3)), key=lambda r: r[0])
+    dt_fp, ok_fp, dt_fp_local = min((e2e_run("footprint", Wm, K) for _ in range(3)), key=lambda r: r[0])
     launches_e2e = (batch.launch_count - lb) // 3
+    e2e_per_rank = ranks.gather(dt_fp_local * 1e3 / K, device)
+    # measured PCIe traffic of the zero-copy path (NVML RX counter, 20 ms windows) while the same call runs back to
+    # back for ~0.4 s: bytes per step = RX rate / step rate over the same interval
+    pcie = measure_pcie_rx(dev_index, lambda: batch.track_host_ptrs(batch.make_ptr_table(host_ptrs(Wm, K)), K, W, "footprint"),
+                           lambda: batch.set_guess(pos_h[Wm % hp]), K, seconds=0.4) if not args.no_pcie else None
     fr = WS + 64
     cp = (fr + 15) // 16 * 16
-    e2e = {"value": world * n * K / dt_fp, "unit": "frames/s",
+    e2e = {"value": n_all * K / dt_fp, "unit": "frames/s",
            "h2d_bytes_per_step": n * fr * cp, "d2h_bytes_per_step": n * 20,
+           "ms_per_step_per_rank": e2e_per_rank, "pcie_rx_measured": pcie,
            "mode": "footprint streaming from pinned host frames (pt_batch_track_host mode 0): the chained kernel reads "
                    "each video's 109x109 u8 footprint of every step straight from the host frame over PCIe (zero-copy; "
                    "h2d_bytes = the 109 rows x 112-byte aligned spans it touches) and stores every step's result "
@@ -612,8 +721,8 @@ def run_gpu(args, ranks):
                    "host clock around the call, frames and results in host memory",
            "ms_per_step": 1e3 * dt_fp / K, "positions_correct": ok_fp}
     kf = min(K, 8)
-    dt_fr, ok_fr = e2e_run("frames", 1, kf)
-    e2e_frames = {"value": world * n * kf / dt_fr, "unit": "frames/s", "steps": kf,
+    dt_fr, ok_fr, _ = e2e_run("frames", 1, kf)
+    e2e_frames = {"value": n_all * kf / dt_fr, "unit": "frames/s", "steps": kf,
                   "h2d_bytes_per_step": n * H * W, "d2h_bytes_per_step": n * 20,
                   "mode": "whole 1080p u8 frames from pinned host memory, double-buffered (mode 1; PCIe-bound)",
                   "ms_per_step": 1e3 * dt_fr / kf, "positions_correct": ok_fr,
@@ -621,17 +730,22 @@ def run_gpu(args, ranks):
     batch.close()
 
     all_ok = ranks.sum_over_ranks(0.0 if (resident_ok and ok_fp and ok_fr and fullframe_ok) else 1.0, device) == 0.0
-    cpu = cpu_baseline() if (ranks.rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    if strong_obj is not None:
+        all_ok = all_ok and strong_obj["positions_correct"]
+    cpu = cpu_baseline(gpu_sample=gpu_sample) if (ranks.rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    if cpu and cpu.get("gpu_chain_vs_oracle"):
+        all_ok = all_ok and cpu["gpu_chain_vs_oracle"]["ok"]
     if ranks.rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": ms_K / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_K / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(), repeats=len(reps_ms),
+                "config": dict(workload_config(args.scaling, world), repeats=len(reps_ms),
                                l2="inputs larger than L2: each timed step reads a step-slot (531 MB) untouched "
                                   f"since the previous repeat; ring of {slots} slots; L2 flushed between repeats",
                                timing="CUDA events on the launching stream, median over repeats, max over ranks"),
                 "clocks": clocks, "e2e": e2e, "e2e_frames": e2e_frames, "roofline": roofline,
                 "cpu_baseline": cpu, "fullframe_dog": fullframe, "balanced_batch": balanced, "mode_fill": mode_fill,
+                "strong": strong_obj, "ms_K_per_rank": ms_K_per_rank,
                 "gpu_launches": int(timed_launches),
                 "gpu_launches_note": f"{batch_kernel} chains the K steps of the timed region inside "
                                      f"{int(timed_launches)} launch(es) (one CTA per SM hosts two videos; with "
@@ -654,6 +768,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-balanced", action="store_true", help="skip the supplementary 2-videos-per-SM measurement")
     ap.add_argument("--preheat", type=float, default=0.3, help="seconds of untimed identical work before timing")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 256 videos per GPU (default); strong: 256 videos in total, video_id mod world "
+                         "(BASELINE configs[2] as written)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the supplementary strong-scaling measurement (N > 1)")
+    ap.add_argument("--no-pcie", action="store_true", help="skip the NVML PCIe RX measurement of the e2e path")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

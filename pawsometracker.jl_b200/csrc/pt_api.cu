@@ -209,7 +209,7 @@ const pt::Cfg &defaults_from_env()
         cfg.zero_copy = getenv("PT_NO_ZEROCOPY") ? 0 : 1;
         cfg.host_lanes = std::max(0, geti("PT_HOST_LANES", 0));
         cfg.cluster = geti("PT_W45_CLUSTER", 0);
-        cfg.bulk = std::min(2, std::max(0, geti("PT_W45_BULK", 2)));
+        cfg.bulk = geti("PT_W45_BULK", 1) ? 1 : 0;
     });
     return cfg;
 }
@@ -1204,7 +1204,7 @@ int pt_batch_set_option(pt_batch *b, const char *name, int value)
         {"r45_chunks", &pt::Cfg::r45_chunks, 0, 1 << 20}, {"generic_target", &pt::Cfg::generic_target, 1, 1 << 20},
         {"mode_slow", &pt::Cfg::mode_slow, 0, 1},     {"zero_copy", &pt::Cfg::zero_copy, 0, 1},
         {"host_lanes", &pt::Cfg::host_lanes, 0, 1024}, {"cluster", &pt::Cfg::cluster, 0, 8},
-        {"bulk", &pt::Cfg::bulk, 0, 2},
+        {"bulk", &pt::Cfg::bulk, 0, 1},
     };
     for (const Opt &o : opts) {
         if (strcmp(o.name, name) != 0) continue;

@@ -26,7 +26,7 @@ struct Cfg {
     int zero_copy = 1;        // 0: never read pinned host frames in place              (PT_NO_ZEROCOPY)
     int host_lanes = 0;       // host threads of the pageable footprint path, 0 = auto  (PT_HOST_LANES)
     int cluster = 0;          // lone-window cluster kernel: 0 auto, 1 off, 2/4/8 CTAs per window (PT_W45_CLUSTER)
-    int bulk = 2;             // cluster kernel staging: 0 global loads, 1 cp.async.bulk per row, 2 one TMA tile copy (PT_W45_BULK)
+    int bulk = 1;             // cluster kernel staging: 1 = one TMA tile copy per step into shared memory, 0 = global loads (PT_W45_BULK)
 };
 
 // One launch = one (trckr::Tracker)(guess) evaluation for every window of the

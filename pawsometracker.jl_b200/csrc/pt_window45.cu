@@ -799,7 +799,7 @@ dog_rect45_march(const __grid_constant__ WinArgs a, const __grid_constant__ Taps
 //
 // Staging (u8 frames, 16-byte aligned rows): the next window centre lies inside the current window, so the
 // region any next footprint can touch — 153 rows × (slice + 64 + 44) bytes — is known one step ahead.  It is
-// fetched with one cp.async.bulk (TMA) per row into a double-buffered u8 region in shared memory while the
+// fetched with ONE 2-D TMA tile copy into a double-buffered u8 region in shared memory while the
 // current step computes; when the guess is known the footprint is converted u8 → f32 out of shared memory:
 // no global-memory latency on the serial chain.  A window that left the prefetched region (possible only when
 // the guess was outside the frame and got clamped) re-fetches its own region.  Other frames (f32, unaligned)
@@ -850,10 +850,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int mbar, unsigne
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned int mbar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(unsigned int mbar, unsigned int parity)
 {
     unsigned int ok;
@@ -869,13 +865,6 @@ __device__ __forceinline__ void mbar_wait(unsigned int mbar, unsigned int parity
     while (!mbar_try_wait(mbar, parity)) {
         if (clock64() - t0 > (1ll << 32)) __trap();          // ≈ 2 s at 2 GHz
     }
-}
-// One row of a frame → shared memory through the TMA unit (cp.async.bulk → SASS UBLKCP); src, dst and size are
-// multiples of 16 bytes.
-__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void *src, unsigned int bytes, unsigned int mbar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(mbar) : "memory");
 }
 // The whole region of a step in ONE instruction: 2-D TMA tile copy (cp.async.bulk.tensor → SASS UTMALDG) out of the
 // tensor map that describes the resident frames as [rows][pitch] bytes; elements outside the tensor arrive as zeros
@@ -1102,36 +1091,20 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
     int rgn_y0[2] = {0, 0}, rgn_xa[2] = {0, 0};
     unsigned int ph[2] = {0u, 0u}, xph[2] = {0u, 0u};
 
-    // request the region around footprint origin (cfy0, cfxs) of step `ts` (frame `frame`) into buffer `buf`:
-    // use_bulk 2 → one TMA tile copy, use_bulk 1 → one bulk copy per row
-    auto issue_region = [&](int buf, const PixT *frame, int ts, int cfy0, int cfxs) {
+    // request the region around footprint origin (cfy0, cfxs) of step `ts` into buffer `buf`: ONE TMA tile copy
+    // (elements outside the tensor arrive as zeros; everything outside the frame is masked at conversion anyway)
+    auto issue_region = [&](int buf, int ts, int cfy0, int cfxs) {
         const int y0 = cfy0 - WR / 2, xa = (cfxs - WC / 2) & ~15;
         rgn_y0[buf] = y0; rgn_xa[buf] = xa;
-        if (use_bulk == 2) {
-            if (tid == 0) {
-                const unsigned int mb = mbar0 + 8u * (unsigned int)buf;
-                mbar_arrive_expect_tx(mb, (unsigned int)(G::RGN_ROWS * G::SPAN));
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                tma_tile_2d(rgn0 + (unsigned int)(buf * G::RGN_BYTES), &tmap, xa, ts * a.tm_rows_step + v * a.tm_rows_frame + y0, mb);
-            }
-            return;
-        }
-        const int lo = max(xa, 0), hi = min(xa + G::SPAN, a.pitch);
-        const int nb = hi - lo;
-        const int ylo = max(y0, 0), yhi = min(y0 + G::RGN_ROWS, a.H);
-        const unsigned int mb = mbar0 + 8u * (unsigned int)buf;
         if (tid == 0) {
-            if (nb > 0 && yhi > ylo) mbar_arrive_expect_tx(mb, (unsigned int)(nb * (yhi - ylo)));
-            else mbar_arrive(mb);
+            const unsigned int mb = mbar0 + 8u * (unsigned int)buf;
+            mbar_arrive_expect_tx(mb, (unsigned int)(G::RGN_ROWS * G::SPAN));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tma_tile_2d(rgn0 + (unsigned int)(buf * G::RGN_BYTES), &tmap, xa, ts * a.tm_rows_step + v * a.tm_rows_frame + y0, mb);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const int Y = y0 + tid;
-        if (tid < G::RGN_ROWS && nb > 0 && Y >= 0 && Y < a.H)
-            bulk_g2s(rgn0 + (unsigned int)(buf * G::RGN_BYTES + tid * G::SPAN + (lo - xa)),
-                     reinterpret_cast<const unsigned char *>(frame) + (size_t)Y * a.pitch + lo, (unsigned int)nb, mb);
     };
 
-    if (bulk) issue_region(0, frame0, 0, g.x - 1 - (WR / 2) - HW, g.y - 1 - (WC / 2) - HW + xs);
+    if (bulk) issue_region(0, 0, g.x - 1 - (WR / 2) - HW, g.y - 1 - (WC / 2) - HW + xs);
 
     for (int t = 0; t < a.T; ++t) {
         const int par = t & 1;
@@ -1148,7 +1121,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
             mbar_wait(mbar0 + 8u * par, ph[par]); ph[par] ^= 1u;
             if (!covered) {                                                  // (uniform) the window left the prefetched region
                 __syncthreads();                                             // every thread has seen the completed phase
-                issue_region(par, frame, t, fy0, fxs);
+                issue_region(par, t, fy0, fxs);
                 mbar_wait(mbar0 + 8u * par, ph[par]); ph[par] ^= 1u;
             }
             const bool interior = fy0 >= 0 && fy0 + FR <= a.H && xw0 >= 0 && xw0 + 4 * G::NW <= a.W;
@@ -1156,7 +1129,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
             if (interior) convert_slice_u8<C, true>(rb, rgn_y0[par], rgn_xa[par], a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
             else convert_slice_u8<C, false>(rb, rgn_y0[par], rgn_xa[par], a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
             // everything the next step can touch → the other buffer (last read by the previous step's conversion)
-            if (t + 1 < a.T) issue_region(par ^ 1, frame + a.step_stride, t + 1, fy0, fxs);
+            if (t + 1 < a.T) issue_region(par ^ 1, t + 1, fy0, fxs);
         } else {
             stage_rows<FR, G::SFC, G::PINS, true>(frame, a.pitch, a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
             if (t + 1 < a.T) {                                               // warm L2 with the next step's region
@@ -1222,20 +1195,23 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
     cluster_wait();
 }
 
-// How many CTAs share one window for this launch (1 = the per-SM kernels above).
+// How many CTAs share one window for this launch (1 = the per-SM kernels above).  Measured (tools/small_batch_timing.py,
+// 1080p, chained steps): 8 CTAs per window win only for a handful of windows (n = 1: 2.0 vs 2.6 µs per step; at n = 16
+// clusters of 8 no longer pack the GPCs one CTA per SM and 4 CTAs are faster: 2.6 vs 3.0), 4 CTAs up to #SMs/4
+// windows (n = 32: 2.7 µs), 2 CTAs up to #SMs/2 (n = 64: 3.9 µs vs 5.8 for the per-SM kernel).
 static int cluster_size_for(const WinArgs &a, const Cfg &cfg, int n)
 {
     if (cfg.cluster == 1 || a.frame_ptrs) return 1;
     if (cfg.cluster == 2 || cfg.cluster == 4 || cfg.cluster == 8) return cfg.cluster;
     const int sms = cfg.sms;
-    if (8 * n <= sms) return 8;
+    if (16 * n <= sms) return 8;
     if (4 * n <= sms) return 4;
     if (2 * n <= sms) return 2;
     return 1;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda: the library must load
-// on a machine without a driver).  nullptr = unavailable → the row-bulk mode is used instead.
+// on a machine without a driver).  nullptr = unavailable → the cluster kernel stages with global loads instead.
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1260,7 +1236,7 @@ static cudaError_t launch_cluster_t(Args45 k, const Taps45 &tp, int use_bulk, cu
 {
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    if (use_bulk == 2) {
+    if (use_bulk) {
         // the resident frames as one 2-D u8 tensor [rows][pitch]: row of (step t, video v, frame row y) =
         // t·rows_step + v·rows_frame + y.  Needs strides that are whole rows; else fall back to row copies.
         tmap_encode_fn enc = tmap_encoder();
@@ -1279,7 +1255,7 @@ static cudaError_t launch_cluster_t(Args45 k, const Taps45 &tp, int use_bulk, cu
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
-        if (!ok) use_bulk = 1;
+        if (!ok) use_bulk = 0;               // no tensor map (irregular strides, old driver): stage with global loads
     }
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(k.n * C));
@@ -1298,7 +1274,7 @@ static cudaError_t launch_cluster(const Args45 &k, const Taps45 &tp, const Cfg &
     // the TMA path needs 16-byte aligned rows
     const bool aligned16 = pixel == 0 && ((reinterpret_cast<uintptr_t>(k.frames) | (uintptr_t)k.pitch | (uintptr_t)k.frame_stride |
                                            (uintptr_t)k.step_stride) & 15u) == 0;
-    const int use_bulk = (cfg.bulk && aligned16) ? cfg.bulk : 0;        // 1: one bulk copy per region row, 2: one TMA tile copy
+    const int use_bulk = (cfg.bulk && aligned16) ? 1 : 0;              // the TMA path needs 16-byte aligned rows
     if (pixel == 0) {
         if (C == 2) return launch_cluster_t<uint8_t, 2>(k, tp, use_bulk, s);
         if (C == 4) return launch_cluster_t<uint8_t, 4>(k, tp, use_bulk, s);

@@ -22,9 +22,10 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 # Response tolerance of the exact-tie tests.  A texture whose period is below the 45-px window lies far outside the
 # pass band of the DoG (σ = 10.6 px): max|R| is only 1e-4 … 1e-3 of the pixel contrast, so the FP32 rounding floor
-# (≈ 1e-8 absolute for pixels in [0, 1], the same floor as everywhere else) is no longer small against max|R|.  The
-# tie DECISION is what these tests pin; the response is held to RTOL·max|R| or this absolute floor.
-ABS_FLOOR = 1e-7
+# (a few 1e-8 absolute for pixels in [0, 1]: ≈ 2^-23 of Σ|tap|·|pixel − fill|, the same floor as everywhere else; worst
+# seen over whole response maps: 1.2e-7) is no longer small against max|R|.  The tie DECISION is what these tests pin;
+# the response is held to RTOL·max|R| or this absolute floor.
+ABS_FLOOR = 3e-7
 
 
 def disk_frame(H, W, cy, cx, r, val=0, bg=128):
@@ -63,10 +64,10 @@ def _cluster_case(synth, H, W, n, T, seed):
 
 
 @pytest.mark.parametrize("C", [2, 4, 8])
-@pytest.mark.parametrize("bulk", [0, 1, 2])
+@pytest.mark.parametrize("bulk", [0, 1])
 def test_cluster_kernel_equals_per_sm_kernel_and_oracle(gpu_pkg, oracle, synth, C, bulk):
     """One window over a cluster of C CTAs (column slices, argmax through DSMEM) with global-load staging (0),
-    cp.async.bulk rows (1) or one TMA tile per step (2): positions AND responses bit-identical to
+    or one TMA tile copy per step into a shared-memory u8 region (1): positions AND responses bit-identical to
     dog_window45_argmax (same per-output operation order), positions equal to the oracle loop."""
     import torch
     n, T, H, W = 5, 9, 200, 256
@@ -132,17 +133,17 @@ def test_cluster_kernel_f32_and_unaligned_frames(gpu_pkg, oracle, synth, C):
 
 
 def test_cluster_size_policy(gpu_pkg):
-    """Auto policy: as many CTAs per window as fit one per SM (8, 4, 2), the per-SM kernels from #SMs/2 windows up."""
+    """Auto policy: 8 CTAs per window up to #SMs/16 windows, 4 up to #SMs/4, 2 up to #SMs/2, then the per-SM kernels."""
     import torch
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     H, W, T = 64, 64, 2
-    for n in (1, sms // 8, sms // 8 + 1, sms // 4, sms // 4 + 1, sms // 2, sms // 2 + 1, sms):
+    for n in (1, sms // 16, sms // 16 + 1, sms // 4, sms // 4 + 1, sms // 2, sms // 2 + 1, sms):
         dev = torch.full((T, n, H, W), 128, dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
         with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
             b.set_fill(128); b.set_guess(np.tile([32, 32], (n, 1)))
             b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
-            want = ("dog_window45_cluster<8>" if 8 * n <= sms else "dog_window45_cluster<4>" if 4 * n <= sms else
+            want = ("dog_window45_cluster<8>" if 16 * n <= sms else "dog_window45_cluster<4>" if 4 * n <= sms else
                     "dog_window45_cluster<2>" if 2 * n <= sms else "dog_window45_argmax")
             assert b.last_kernel == want, (n, b.last_kernel)
 

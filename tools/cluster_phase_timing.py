@@ -22,7 +22,7 @@ for n in [int(x) for x in sys.argv[1:]] or [1, 32]:
     b.bind_device_frames(ring.data_ptr(), H * W, W); b.set_fill(128)
     ext = torch.cuda.ExternalStream(b.stream, device=dev)
     for Cc in (1, 2, 4, 8):
-        for bulk in ((0,) if Cc == 1 else (0, 2)):
+        for bulk in ((0,) if Cc == 1 else (0, 1)):
             b.set_option("cluster", Cc); b.set_option("bulk", bulk)
             for rep in range(3):
                 flush.fill_(1)

@@ -1,7 +1,7 @@
 """Chained tracking of small batches (n <= #SMs): frames resident in HBM, T steps per launch, CUDA events, L2 flushed
 before every launch.  Sweeps the lone-window options: the per-SM kernel (cluster=1), the cluster kernel with 2 / 4 / 8
-CTAs per window and its three staging modes (bulk 0 = global loads + L2 prefetch, 1 = cp.async.bulk per region row,
-2 = one TMA tile copy per step), and the automatic choice.
+CTAs per window and its two staging modes (bulk 0 = global loads + L2 prefetch, 1 = one TMA tile copy per step),
+and the automatic choice.
 Usage: python tools/small_batch_timing.py [--T 20,100] [n ...]"""
 import os, sys
 import numpy as np
@@ -27,10 +27,10 @@ for n in ns:
     b = pkg.TrackerBatch(n, (H, W), bench.TW, (bench.WS, bench.WS), True)
     b.bind_device_frames(ring.data_ptr(), H * W, W); b.set_fill(128)
     ext = torch.cuda.ExternalStream(b.stream, device=dev)
-    variants = [("auto", 0, 2), ("per-SM", 1, 0)]
+    variants = [("auto", 0, 1), ("per-SM", 1, 0)]
     for C in (2, 4, 8):
         if n * C <= 4 * sms:
-            variants += [(f"C={C} bulk=2", C, 2), (f"C={C} bulk=1", C, 1), (f"C={C} bulk=0", C, 0)]
+            variants += [(f"C={C} bulk=1", C, 1), (f"C={C} bulk=0", C, 0)]
     for name, C, bulk in variants:
         b.set_option("cluster", C); b.set_option("bulk", bulk)
         row = []
