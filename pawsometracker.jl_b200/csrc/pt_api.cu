@@ -210,6 +210,7 @@ const pt::Cfg &defaults_from_env()
         cfg.host_lanes = std::max(0, geti("PT_HOST_LANES", 0));
         cfg.cluster = geti("PT_W45_CLUSTER", 0);
         cfg.bulk = geti("PT_W45_BULK", 1) ? 1 : 0;
+        cfg.wide = geti("PT_GENERIC_WIDE", 1) ? 1 : 0;
     });
     return cfg;
 }
@@ -229,6 +230,7 @@ int device_info(int device, DeviceInfo *out)
         int sms = 0;
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         CU(pt::generic_init_device());
+        CU(pt::wide_init_device());
         CU(pt::window45_init_device());
         d.sms = sms > 0 ? sms : 148;
         d.ready = true;
@@ -355,13 +357,22 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     return a;
 }
 
+// the 64-column kernel: windows wider than one 32-column strip whose kernel length fits its shared-memory footprint
+bool use_wide_kernel(const pt_batch *b, const pt::WinArgs &a)
+{
+    return b->cfg.wide && a.wc > pt::kTileCols && a.L <= pt::wide_max_kernel_len() &&
+           pt::wide_smem_bytes(a.L) + 512 <= (size_t)b->cfg.smem_optin;
+}
+
 void decompose(pt::WinArgs &a, int nwin, int target)
 {
     // Strips of 32 output columns; row chunks only where a launch would otherwise leave the GPU
     // under-occupied.  Each extra chunk repeats 2w footprint rows of the row pass, so chunks are
     // added until ~kTarget CTAs exist (measured best for the 1080p full-frame shape) and never below
     // one batch of rows.
-    a.strips = (a.wc + pt::kTileCols - 1) / pt::kTileCols;
+    const int tile_cols = a.wide ? 2 * pt::kTileCols : pt::kTileCols;
+    a.strips = (a.wc + tile_cols - 1) / tile_cols;
+    if (a.wide) target = std::max(1, target / 4);       // one 256-thread CTA per SM (or two) instead of four 128-thread ones
     const int total = nwin * a.strips;
     int chunks = 1;
     if (total < target) {
@@ -381,16 +392,18 @@ cudaError_t launch_windows(const pt_batch *b, pt::WinArgs &a, int nwin, cudaStre
         return pt::launch_window45(a, b->cfg, nwin, b->pixel, s);
     if (b->cfg.window45 && pt::rect45_supported(a, b->cfg, b->pixel))
         return pt::launch_rect45(a, b->cfg, nwin, b->pixel, s);
+    a.wide = use_wide_kernel(b, a) ? 1 : 0;
     decompose(a, nwin, b->cfg.generic_target);
-    return pt::launch_generic(a, nwin, b->pixel, s);
+    return a.wide ? pt::launch_wide(a, nwin, b->pixel, s) : pt::launch_generic(a, nwin, b->pixel, s);
 }
 
 int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
 {
     const cudaError_t e = launch_windows(b, a, nwin, s);
     if (b->cfg.window45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
-        b->last_kernel = pt::window45_kernel_for(a, b->cfg, nwin);
+        b->last_kernel = pt::window45_kernel_for(a, b->cfg, nwin, b->pixel);
     else if (b->cfg.window45 && pt::rect45_supported(a, b->cfg, b->pixel)) b->last_kernel = pt::rect45_name();
+    else if (use_wide_kernel(b, a)) b->last_kernel = b->pixel == PT_PIX_U8 ? "dog_rect_argmax_wide<u8>" : "dog_rect_argmax_wide<f32>";
     else b->last_kernel = b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     b->launches += 1;
@@ -595,6 +608,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
     b->L = L; b->w = L / 2; b->Lpad = Lpad;
     b->cfg = defaults_from_env();
     b->cfg.sms = dinfo.sms;
+    b->cfg.smem_optin = smem_optin;
     configure_window(b, ws_rows, ws_cols);
     b->own_pitch = pixel == PT_PIX_U8 ? (((size_t)W + 15) & ~(size_t)15) : (((size_t)W + 3) & ~(size_t)3);
     b->own_stride = b->own_pitch * (size_t)H;
@@ -1205,6 +1219,7 @@ int pt_batch_set_option(pt_batch *b, const char *name, int value)
         {"mode_slow", &pt::Cfg::mode_slow, 0, 1},     {"zero_copy", &pt::Cfg::zero_copy, 0, 1},
         {"host_lanes", &pt::Cfg::host_lanes, 0, 1024}, {"cluster", &pt::Cfg::cluster, 0, 8},
         {"bulk", &pt::Cfg::bulk, 0, 1},
+        {"wide", &pt::Cfg::wide, 0, 1},
     };
     for (const Opt &o : opts) {
         if (strcmp(o.name, name) != 0) continue;

@@ -26,6 +26,8 @@ struct Cfg {
     int zero_copy = 1;        // 0: never read pinned host frames in place              (PT_NO_ZEROCOPY)
     int host_lanes = 0;       // host threads of the pageable footprint path, 0 = auto  (PT_HOST_LANES)
     int cluster = 0;          // lone-window cluster kernel: 0 auto, 1 off, 2/4/8 CTAs per window (PT_W45_CLUSTER)
+    int wide = 1;             // 1: dog_rect_argmax_wide (64-column strips) where it fits, 0: always the 32-column kernel (PT_GENERIC_WIDE)
+    int smem_optin = 0;       // largest dynamic shared memory per block the device allows (set at create)
     int bulk = 1;             // cluster kernel staging: 1 = one TMA tile copy per step into shared memory, 0 = global loads (PT_W45_BULK)
 };
 
@@ -46,6 +48,7 @@ struct WinArgs {
     const float2 *taps_row;    // [Lpad] (narrow, wide) row-pass taps (pixel scale folded in)
     const float2 *taps_col;    // [Lpad] (narrow, wide) column-pass taps (sign folded in)
     int strips, chunks, CH;    // CTA decomposition of one window
+    int wide;                  // 0: 32-column strips (dog_rect_argmax_generic); 1: 64-column strips (dog_rect_argmax_wide)
     unsigned long long *keys;  // [n] packed running argmax (zero between launches)
     unsigned int *counters;    // [n] CTA completion counters (zero between launches)
     unsigned int *tickets;     // [2] work-ticket counter + finished-halves counter of dog_rect45_march (zero between launches)
@@ -113,11 +116,18 @@ cudaError_t window45_init_device();
 size_t generic_smem_bytes(int L, int Lpad);
 cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s);
 
+// The same filter with 64-column strips and integer-free inner loops (pt_generic64.cu); needs more shared memory per
+// CTA (l up to ≈ 285), the 32-column kernel above covers longer kernels and narrow windows.
+int wide_max_kernel_len();
+size_t wide_smem_bytes(int L);
+cudaError_t wide_init_device();
+cudaError_t launch_wide(const WinArgs &a, int n, int pixel, cudaStream_t s);
+
 // Specialised batched kernel: l = 65 (target_width 25), 45×45 window.
 bool window45_supported(const WinArgs &a, int pixel);
 cudaError_t launch_window45(const WinArgs &a, const Cfg &cfg, int n, int pixel, cudaStream_t s);
 // name of the kernel launch_window45 would run for this launch (dog_window45_argmax / _rot / _cluster<C>)
-const char *window45_kernel_for(const WinArgs &a, const Cfg &cfg, int n);
+const char *window45_kernel_for(const WinArgs &a, const Cfg &cfg, int n, int pixel);
 const char *window45_name();
 #ifdef PT_PROBES
 void window45_set_debug(long long *dev_buf);   // phase-timestamp buffer [n][T][6] (profiling build only)

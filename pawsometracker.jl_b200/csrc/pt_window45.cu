@@ -248,6 +248,87 @@ __device__ __forceinline__ void stage_tile(const PixT *frame, int pitch, int H, 
     stage_rows<FR>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
 }
 
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned int mbar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int mbar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned int mbar, unsigned int parity)
+{
+    unsigned int ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// Wait for the phase with the given parity; a watchdog turns a lost copy into a launch error instead of a hang.
+__device__ __forceinline__ void mbar_wait(unsigned int mbar, unsigned int parity)
+{
+    if (mbar_try_wait(mbar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(mbar, parity)) {
+        if (clock64() - t0 > (1ll << 32)) __trap();          // ≈ 2 s at 2 GHz
+    }
+}
+// u8 → f32 conversion of footprint rows out of raw u8 rows in shared memory (filled by TMA): the same word / PRMT /
+// 2^23 scheme as stage_rows_u8, LDS instead of LDG.  Warp w converts the contiguous rows [14w, 14w + 14).  raw row 0 ↔
+// frame row raw_y0, raw byte 0 ↔ frame column raw_xa (a multiple of 16), SPAN bytes per raw row.  Bytes outside the
+// frame were never copied (or arrived as zeros): they are replaced by the fill byte.
+template <int SPAN, int FCOLS, int PITCH, bool kInterior>
+__device__ __forceinline__ void convert_rows_u8(const uint8_t *raw, int raw_y0, int raw_xa, int H, int W, int fy0, int fx0,
+                                                float fill, float *s_in, int warp, int lane)
+{
+    constexpr int RPW = (FR + NWARPS - 1) / NWARPS;
+    const int xw0 = fx0 & ~3, phase = fx0 - xw0;
+    const int X = xw0 + 4 * lane;
+    const unsigned int fillw = (unsigned int)fill * 0x01010101u;
+    unsigned int keep = 0xFFFFFFFFu;
+    if (!kInterior) {
+        keep = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < W) keep |= 0xFFu << (8 * b);
+    }
+    const bool wordok = keep != 0u && (4 * lane - phase < FCOLS);
+    const int rot = lane >> 3;
+    int col[4];
+    bool cok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        col[k] = 4 * lane - phase + ((k + rot) & 3);
+        cok[k] = col[k] >= 0 && col[k] < FCOLS;
+    }
+    unsigned int wd[RPW];
+    const int f0 = warp * RPW;
+    const uint8_t *src = raw + (fy0 + f0 - raw_y0) * SPAN + (X - raw_xa);
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int f = f0 + r;
+        const int Y = fy0 + f;
+        const bool ok = wordok && (f < FR) && (kInterior || ((Y >= 0) && (Y < H)));
+        wd[r] = fillw;
+        if (ok) wd[r] = *reinterpret_cast<const unsigned int *>(src + r * SPAN);
+    }
+    const float cst = 8388608.0f + fill;
+    const unsigned int magic = 0x4B000000u;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int f = f0 + r;
+        if (f < FR) {
+            unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
+            w = __funnelshift_r(w, w, 8 * rot);
+            float *dst = s_in + f * PITCH;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float val = __uint_as_float(__byte_perm(w, magic, c_prmt_sel[k])) - cst;
+                if (cok[k]) dst[col[k]] = val;
+            }
+        }
+    }
+}
+
 } // namespace
 
 
@@ -390,6 +471,9 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);   // window origin, 0-based
         const int fy0 = wy0 - HW, fx0 = wx0 - HW;                        // footprint origin
 
+        // (Fetching the footprint rows of zero-copy HOST frames with one cp.async.bulk per row instead of these lane
+        // loads was measured and dropped: NVML counted 11.4 MB of PCIe reads per 256-window step instead of 5.8 MB,
+        // the link saturated at 61 GB/s and the step took 147 µs instead of 111 µs.)
         stage_tile<PixT>(frame, a.pitch, a.H, a.W, fy0, fx0, fill, s_in, warp, lane);
 
         // ---- warm L2 with everything the NEXT step can touch: its window centre is inside this
@@ -841,31 +925,6 @@ struct SliceGeom {
 };
 constexpr int CL_THREADS = 256;
 
-__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned int mbar, unsigned int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int mbar, unsigned int bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned int mbar, unsigned int parity)
-{
-    unsigned int ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
-    return ok != 0u;
-}
-// Wait for the phase with the given parity; a watchdog turns a lost copy into a launch error instead of a hang.
-__device__ __forceinline__ void mbar_wait(unsigned int mbar, unsigned int parity)
-{
-    if (mbar_try_wait(mbar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(mbar, parity)) {
-        if (clock64() - t0 > (1ll << 32)) __trap();          // ≈ 2 s at 2 GHz
-    }
-}
 // The whole region of a step in ONE instruction: 2-D TMA tile copy (cp.async.bulk.tensor → SASS UTMALDG) out of the
 // tensor map that describes the resident frames as [rows][pitch] bytes; elements outside the tensor arrive as zeros
 // (and are masked by frame coordinates anyway).
@@ -896,61 +955,14 @@ __device__ __forceinline__ void st_async_u64(unsigned int local_addr, unsigned i
                  ::"r"(mapa_u32(local_addr, rank)), "l"(v), "r"(mapa_u32(local_mbar, rank)) : "memory");
 }
 
-// u8 → f32 conversion of the footprint rows of one warp (rows [warp·14, warp·14 + 14)) out of the prefetched u8 region
-// in shared memory: the same word / PRMT / 2^23 scheme as stage_rows_u8, LDS instead of LDG.  rgn row 0 ↔ frame row
-// rgn_y0, rgn byte 0 ↔ frame column rgn_xa (multiple of 16).  Bytes outside the frame were never copied: they are
-// replaced by the fill byte.  (Flattening the (row, word) pairs over all lanes was measured: no gain, more registers.)
+// (conversion of a slice out of the prefetched region: convert_rows_u8 with the slice geometry.  Flattening the
+// (row, word) pairs over all lanes was measured: no gain, more registers.)
 template <int C, bool kInterior>
 __device__ __forceinline__ void convert_slice_u8(const uint8_t *rgn, int rgn_y0, int rgn_xa, int H, int W, int fy0, int fxs,
                                                  float fill, float *s_in, int warp, int lane)
 {
     using G = SliceGeom<C>;
-    constexpr int RPW = G::RPW;
-    const int xw0 = fxs & ~3, phase = fxs - xw0;
-    const int X = xw0 + 4 * lane;
-    const unsigned int fillw = (unsigned int)fill * 0x01010101u;
-    unsigned int keep = 0xFFFFFFFFu;
-    if (!kInterior) {
-        keep = 0u;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < W) keep |= 0xFFu << (8 * b);
-    }
-    const bool wordok = keep != 0u && (4 * lane - phase < G::SFC);
-    const int rot = lane >> 3;
-    int col[4];
-    bool cok[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        col[k] = 4 * lane - phase + ((k + rot) & 3);
-        cok[k] = col[k] >= 0 && col[k] < G::SFC;
-    }
-    unsigned int wd[RPW];
-    const int f0 = warp * RPW;
-    const uint8_t *src = rgn + (fy0 + f0 - rgn_y0) * G::SPAN + (X - rgn_xa);
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int f = f0 + r;
-        const int Y = fy0 + f;
-        const bool ok = wordok && (f < FR) && (kInterior || ((Y >= 0) && (Y < H)));
-        wd[r] = fillw;
-        if (ok) wd[r] = *reinterpret_cast<const unsigned int *>(src + r * G::SPAN);
-    }
-    const float cst = 8388608.0f + fill;
-    const unsigned int magic = 0x4B000000u;
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int f = f0 + r;
-        if (f < FR) {
-            unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
-            w = __funnelshift_r(w, w, 8 * rot);
-            float *dst = s_in + f * G::PINS;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float val = __uint_as_float(__byte_perm(w, magic, c_prmt_sel[k])) - cst;
-                if (cok[k]) dst[col[k]] = val;
-            }
-        }
-    }
+    convert_rows_u8<G::SPAN, G::SFC, G::PINS, kInterior>(rgn, rgn_y0, rgn_xa, H, W, fy0, fxs, fill, s_in, warp, lane);
 }
 
 // Row pass of a slice over the 14 rows THIS WARP staged (no CTA barrier between staging and row pass: warps run
@@ -1087,7 +1099,9 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
 
     const float fill = a.fill[v];
     int2 g = a.guess[v];
-    const PixT *frame0 = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
+    // frames: resident in HBM (base + strides) or, zero-copy, a table of page-locked host frames (staged with global
+    // loads over PCIe: each CTA reads the rows of its slice)
+    const PixT *frame0 = a.frame_ptrs ? nullptr : reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
     int rgn_y0[2] = {0, 0}, rgn_xa[2] = {0, 0};
     unsigned int ph[2] = {0u, 0u}, xph[2] = {0u, 0u};
 
@@ -1111,7 +1125,8 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
         PT_PROBE_BEGIN(a, v, t, tid + rank)
         // this step's candidates: 8 bytes from every warp of every CTA of the cluster (this CTA's own included)
         if (tid == 0) mbar_arrive_expect_tx(xbar0 + 8u * par, 8u * NWARPS * C);
-        const PixT *frame = frame0 + (size_t)t * a.step_stride;
+        const PixT *frame = a.frame_ptrs ? reinterpret_cast<const PixT *>(a.frame_ptrs[(size_t)t * a.n + v])
+                                         : frame0 + (size_t)t * a.step_stride;
         const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);
         const int fy0 = wy0 - HW, fxs = wx0 - HW + xs;                       // footprint origin of this slice
         if (bulk) {
@@ -1132,7 +1147,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
             if (t + 1 < a.T) issue_region(par ^ 1, t + 1, fy0, fxs);
         } else {
             stage_rows<FR, G::SFC, G::PINS, true>(frame, a.pitch, a.H, a.W, fy0, fxs, fill, s_in, warp, lane);
-            if (t + 1 < a.T) {                                               // warm L2 with the next step's region
+            if (t + 1 < a.T && !a.frame_ptrs) {                              // warm L2 with the next step's region
                 const PixT *nframe = frame + a.step_stride;
                 constexpr int NLMAX = (int)(((G::SFC + WC) * sizeof(PixT) + 127) / 128) + 1;
                 const int pxb = (fxs - WC / 2) * (int)sizeof(PixT);
@@ -1201,9 +1216,16 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
 // windows (n = 32: 2.7 µs), 2 CTAs up to #SMs/2 (n = 64: 3.9 µs vs 5.8 for the per-SM kernel).
 static int cluster_size_for(const WinArgs &a, const Cfg &cfg, int n)
 {
-    if (cfg.cluster == 1 || a.frame_ptrs) return 1;
+    if (cfg.cluster == 1) return 1;
     if (cfg.cluster == 2 || cfg.cluster == 4 || cfg.cluster == 8) return cfg.cluster;
     const int sms = cfg.sms;
+    if (a.frame_ptrs) {
+        // zero-copy host frames: every CTA of a cluster pulls its own slice rows over PCIe (C = 4: 3.5x the bytes of
+        // one footprint), which is free for a handful of windows and costs bandwidth for many
+        if (16 * n <= sms) return 4;
+        if (4 * n <= sms) return 2;
+        return 1;
+    }
     if (16 * n <= sms) return 8;
     if (4 * n <= sms) return 4;
     if (2 * n <= sms) return 2;
@@ -1272,8 +1294,9 @@ static cudaError_t launch_cluster_t(Args45 k, const Taps45 &tp, int use_bulk, cu
 static cudaError_t launch_cluster(const Args45 &k, const Taps45 &tp, const Cfg &cfg, int C, int pixel, cudaStream_t s)
 {
     // the TMA path needs 16-byte aligned rows
-    const bool aligned16 = pixel == 0 && ((reinterpret_cast<uintptr_t>(k.frames) | (uintptr_t)k.pitch | (uintptr_t)k.frame_stride |
-                                           (uintptr_t)k.step_stride) & 15u) == 0;
+    const bool aligned16 = pixel == 0 && !k.frame_ptrs &&
+                           ((reinterpret_cast<uintptr_t>(k.frames) | (uintptr_t)k.pitch | (uintptr_t)k.frame_stride |
+                             (uintptr_t)k.step_stride) & 15u) == 0;
     const int use_bulk = (cfg.bulk && aligned16) ? 1 : 0;              // the TMA path needs 16-byte aligned rows
     if (pixel == 0) {
         if (C == 2) return launch_cluster_t<uint8_t, 2>(k, tp, use_bulk, s);
@@ -1373,7 +1396,7 @@ static bool uses_rot(const WinArgs &a, const Cfg &cfg, int n)
     return cfg.rot && a.xflag && a.xpos && !a.frame_ptrs && a.T > 1 && n > sms && n < 2 * sms && few_holes;
 }
 
-const char *window45_kernel_for(const WinArgs &a, const Cfg &cfg, int n)
+const char *window45_kernel_for(const WinArgs &a, const Cfg &cfg, int n, int pixel)
 {
     const int C = cluster_size_for(a, cfg, n);
     if (C == 2) return "dog_window45_cluster<2>";

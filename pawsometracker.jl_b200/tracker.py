@@ -113,7 +113,7 @@ class TrackerBatch:
 
     def set_option(self, name: str, value: int):
         """Per-handle tuning / debugging knob (pt_batch_set_option): "window45", "rect45", "rot", "skew",
-        "r45_chunks", "generic_target", "mode_slow", "zero_copy", "host_lanes", "cluster", "bulk"."""
+        "r45_chunks", "generic_target", "mode_slow", "zero_copy", "host_lanes", "cluster", "bulk", "wide"."""
         check(lib.pt_batch_set_option(self._h, name.encode(), int(value)))
 
     def set_frames(self, frames):

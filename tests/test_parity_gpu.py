@@ -423,7 +423,14 @@ def test_zero_copy_pinned_host_frames(gpu_pkg, oracle, synth):
         lc = b.launch_count
         ij_zc, r_zc = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
         assert b.launch_count - lc == 1, "pinned frames must take the single-launch zero-copy path"
+        assert b.last_kernel == "dog_window45_cluster<4>"              # 5 videos: lone-window kernel, zero-copy rows
         nxt, _ = b.step(None)                                          # chain state was left on the device
+        b.set_option("cluster", 1)                                     # the same through the per-SM kernel
+        b.set_guess(start)
+        ij_ll, r_ll = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+        assert b.last_kernel == "dog_window45_argmax"
+        np.testing.assert_array_equal(ij_ll, ij_zc)
+        np.testing.assert_array_equal(r_ll, r_zc)
         b.set_option("zero_copy", 0)
         b.set_guess(start)
         ij_staged, _ = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")

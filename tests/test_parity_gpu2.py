@@ -520,3 +520,50 @@ def test_downscale_against_opencv_bilinear(gpu_pkg):
             got = b.downscale(360, 640)[0]
         ref = cv2.resize(base, (640, 360), interpolation=cv2.INTER_LINEAR)
         assert np.abs(got.astype(int) - ref.astype(int)).max() <= 1
+
+
+# ---------------------------------------------------------------------------
+# dog_rect_argmax_wide (64-column strips, integer-free inner loops) vs the 32-column kernel and the oracle
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("tw,ws,darker,dtype", [
+    (100, (173, 173), False, np.uint8),      # BASELINE config 4 geometry (l = 245, δ = 4), default window
+    (100, (97, 130), False, np.float32),
+    (10, (75, 99), True, np.uint8),          # l = 29 (δ = 4)
+    (33, (61, 161), True, np.uint8),         # l = 81 (δ = 0)
+    (50, (129, 65), False, np.uint8),        # l = 121 (δ = 0), two strips, the second one column wide
+    (7, (33, 200), True, np.float32),        # l = 21, four strips
+])
+def test_wide_generic_kernel_equals_narrow_and_oracle(gpu_pkg, oracle, tw, ws, darker, dtype):
+    """Both generic kernels perform the same operations per output in the same order: bit-identical response maps;
+    the map matches the f64 oracle within RTOL.  Windows hang over the frame edge; several row chunks per strip."""
+    l = oracle.kernel_len(tw)
+    rng = np.random.default_rng(int(tw) * 7 + ws[0])
+    H, W = ws[0] + l // 2 + 60, ws[1] + l // 2 + 50
+    cy, cx = H // 2 + 9, W // 2 - 11
+    f8 = disk_frame(H, W, cy, cx, max(2, int(tw) // 2), val=0 if darker else 255)
+    f8 = np.clip(f8.astype(int) + rng.integers(-5, 6, f8.shape), 0, 255).astype(np.uint8)
+    frame = f8 if dtype is np.uint8 else f8.astype(np.float32) / np.float32(255.0)
+    guess = (cy - 6, cx + 8)
+    fill = oracle.mode(f8)
+    ref = oracle.step(f8, fill, tw, darker, ws, guess, dense=False, want_map=True)
+    maps, outs = {}, {}
+    for wide in (1, 0):
+        for target in (592, 2000):                                   # 2000: more row chunks per strip
+            trk = gpu_pkg.Tracker(frame, tw, ws, darker)
+            try:
+                trk.set_option("wide", wide); trk.set_option("generic_target", target)
+                assert trk.fillvalue == fill
+                outs[wide, target] = (trk.step_resident(guess), trk.last_response)
+                maps[wide, target] = trk.response_map(guess)
+                name = trk._batch.last_kernel
+                assert name.startswith("dog_rect_argmax_wide" if wide else "dog_rect_argmax_generic"), name
+            finally:
+                trk.close()
+    base = maps[1, 592]
+    assert np.abs(base.astype(np.float64) - ref.R).max() <= RTOL * ref.maxabs
+    for k, m in maps.items():
+        np.testing.assert_array_equal(m, base, err_msg=str(k))
+        assert outs[k] == outs[1, 592]
+    if not ref.near_tie(RTOL):
+        assert outs[1, 592][0] == (ref.i, ref.j)
+    assert abs(outs[1, 592][1] - ref.resp) <= RTOL * ref.maxabs

@@ -10,9 +10,13 @@ dev = torch.device("cuda", 0)
 f = np.full((H, W), 128, np.uint8)
 yy, xx = np.ogrid[0:H, 0:W]
 f[(yy - 1000) ** 2 + (xx - 2000) ** 2 <= 2500] = 255
-for n in (1, 16, 64):
-    for ws in (173, 401):
+cases = [(n, ws, wide) for n in (1, 16, 64) for ws in (173, 401) for wide in (1, 0)]
+if len(sys.argv) == 4:                      # one case: n ws wide   (for ncu)
+    cases = [tuple(int(x) for x in sys.argv[1:4])]
+for n, ws, wide in cases:
+    if True:
         b = pkg.TrackerBatch(n, (H, W), 100, (ws, ws), False)
+        b.set_option("wide", wide)
         b.set_frames([f] * n); b.set_fill(128)
         ext = torch.cuda.ExternalStream(b.stream, device=dev)
         g = np.tile([1010, 1990], (n, 1))
@@ -29,6 +33,6 @@ for n in (1, 16, 64):
         l = 245; w = 122; wr = 2 * (ws // 2) + 1
         mac = 2 * l * wr * (wr + 2 * w + wr)
         t = min(ts) * 1e-3
-        print(f"{b.kernel_name} n={n} ws={ws}: {t*1e6:.1f} us ({t*1e6/n:.1f} us/window), result {o[0][0]}, "
+        print(f"{b.last_kernel} n={n} ws={ws}: {t*1e6:.1f} us ({t*1e6/n:.1f} us/window), result {o[0][0]}, "
               f"{n*2*mac/t/1e12:.1f} TFLOP/s algorithmic")
         b.close()

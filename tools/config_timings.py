@@ -23,11 +23,26 @@ def config_track(label, H, W, nfr, tw, darker, start_location, window_size=None)
     tra = synth.spiral(0.8 * min(H, W) / 2, 3000, start, seed=0)[:nfr]          # the 3000-frame spiral of the configs
     vid = synth.SyntheticVideo(H, W, tra, tw, darker, fps=24.0)
     frames = np.stack([vid.frame(k) for k in range(nfr)])
-    av = pkg.ArrayVideo(frames, fps=24.0)
-    dt, (ts, ij) = timed(label, lambda: pkg.track(av, stop=nfr / 24.0, target_width=tw, start_location=start_location,
-                                                   window_size=window_size, darker_target=darker, fps=24))
-    err = np.sqrt(np.mean(np.sum((ij - tra[:len(ij)]) ** 2, axis=1)))
-    print(f"{label}: {len(ij)} frames in {dt*1e3:.1f} ms = {len(ij)/dt:.0f} frames/s ({dt/len(ij)*1e6:.1f} us/frame), RMSE {err:.2f} px")
+    ref = None
+    for where in ("pageable", "page-locked"):
+        # page-locked: the decoder's output buffer is pt_host_alloc memory (PinnedArray) — the kernels read the
+        # footprints in place (zero-copy), one chained launch per 64-frame chunk; pageable: the library gathers each
+        # footprint into pinned staging per step
+        pin = None
+        if where == "page-locked":
+            pin = pkg.PinnedArray(frames.shape, np.uint8)
+            pin.array[...] = frames
+        av = pkg.ArrayVideo(pin.array if pin else frames, fps=24.0)
+        dt, (ts, ij) = timed(label, lambda: pkg.track(av, stop=nfr / 24.0, target_width=tw, start_location=start_location,
+                                                       window_size=window_size, darker_target=darker, fps=24))
+        err = np.sqrt(np.mean(np.sum((ij - tra[:len(ij)]) ** 2, axis=1)))
+        same = "" if ref is None else f", identical to pageable: {bool(np.array_equal(ij, ref))}"
+        ref = ij if ref is None else ref
+        print(f"{label} [{where} frames]: {len(ij)} frames in {dt*1e3:.1f} ms = {len(ij)/dt:.0f} frames/s "
+              f"({dt/len(ij)*1e6:.1f} us/frame), RMSE {err:.2f} px{same}", flush=True)
+        if pin:
+            del av
+            pin.close()
     return frames, tra
 
 
@@ -48,7 +63,7 @@ print(f"Tracker.step_resident (whole-frame upload + step): {dt*1e6:.1f} us/call 
 trk.close()
 
 config_track("config 1: 480x640, 300 frames, tw=25, start given", 480, 640, 300, 25, True, pkg.CartesianIndex(240, 320))
-config_track("config 2: 1080p, 600 of 3000 frames, tw=25, start missing (auto-detect)", 1080, 1920, 600, 25, True, None)
+config_track("config 2: 1080p, 1000 of 3000 frames, tw=25, start missing (auto-detect)", 1080, 1920, 1000, 25, True, None)
 config_track("config 4: 4K, 60 frames, light target tw=100, window 401", 2160, 3840, 60, 100, False, None, 401)
 config_track("config 4b: 4K, 60 frames, light target tw=100, default window", 2160, 3840, 60, 100, False, None)
 
