@@ -122,6 +122,15 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2 *>(&rd);
 }
+// max over the warp of 64-bit keys with two 32-bit REDUX (instead of five rounds of 64-bit shuffles)
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long key)
+{
+    const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
+    const unsigned int mh = __reduce_max_sync(0xFFFFFFFFu, hi);
+    const unsigned int ml = __reduce_max_sync(0xFFFFFFFFu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | (unsigned long long)ml;
+}
+
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 {
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
@@ -517,22 +526,14 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         ++round;
         PT_PROBE(3, tid);
 
-        unsigned long long key = col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
-            key = o > key ? o : key;
-        }
+        const unsigned long long key = warp_max_key(col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr));
         if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
         bar_half(half);
         PT_PROBE(4, tid);
         {
-            // every thread folds the 8 warp keys itself (broadcast loads): no serial section;
+            // every warp folds the 8 warp keys itself (lane i reads key i mod 8, two REDUX): no serial section;
             // s_key is double-buffered by iteration parity
-            const unsigned long long *kk = s_key + (it & 1) * NWARPS;
-            unsigned long long k = kk[0];
-#pragma unroll
-            for (int i = 1; i < NWARPS; ++i) k = kk[i] > k ? kk[i] : k;
+            const unsigned long long k = warp_max_key(s_key[(it & 1) * NWARPS + (lane & (NWARPS - 1))]);
             const unsigned int idx = key_index(k);
             const int xx = (int)(idx / WR), yy = (int)(idx - xx * WR);
             const int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;                   // absolute index (:60)
@@ -684,20 +685,14 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
         if (tid == 0) atomicExch(&s_rowlock, 0);
         PT_PROBE(3, tid);
 
-        unsigned long long key = col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
-            key = o > key ? o : key;
-        }
+        const unsigned long long key = warp_max_key(col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr));
         if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
         bar_half(half);
         PT_PROBE(4, tid);
         {
-            const unsigned long long *kk = s_key + (it & 1) * NWARPS;
-            unsigned long long k = kk[0];
-#pragma unroll
-            for (int i = 1; i < NWARPS; ++i) k = kk[i] > k ? kk[i] : k;
+            // every warp folds the 8 warp keys itself (lane i reads key i mod 8, two REDUX): no serial section;
+            // s_key is double-buffered by iteration parity
+            const unsigned long long k = warp_max_key(s_key[(it & 1) * NWARPS + (lane & (NWARPS - 1))]);
             const unsigned int idx = key_index(k);
             const int xx = (int)(idx / WR), yy = (int)(idx - xx * WR);
             const int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;
@@ -1001,15 +996,6 @@ __device__ __forceinline__ void row_pass_slice(const float *s_in, float2 *s_midT
     }
 }
 
-// max over the warp of 64-bit keys with two 32-bit REDUX (instead of five rounds of 64-bit shuffles)
-__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long key)
-{
-    const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
-    const unsigned int mh = __reduce_max_sync(0xFFFFFFFFu, hi);
-    const unsigned int ml = __reduce_max_sync(0xFFFFFFFFu, hi == mh ? lo : 0u);
-    return ((unsigned long long)mh << 32) | (unsigned long long)ml;
-}
-
 // Column pass of a slice + per-thread argmax: item = (slice column x, group h of RC output rows), h fastest.
 // Same per-output operation order as col_pass45 (packed pairs of vertically adjacent outputs, narrow and wide
 // parts accumulated separately, added at the end).  `width` columns of the slice are real; the slice's column 0
@@ -1211,9 +1197,10 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
 }
 
 // How many CTAs share one window for this launch (1 = the per-SM kernels above).  Measured (tools/small_batch_timing.py,
-// 1080p, chained steps): 8 CTAs per window win only for a handful of windows (n = 1: 2.0 vs 2.6 µs per step; at n = 16
-// clusters of 8 no longer pack the GPCs one CTA per SM and 4 CTAs are faster: 2.6 vs 3.0), 4 CTAs up to #SMs/4
-// windows (n = 32: 2.7 µs), 2 CTAs up to #SMs/2 (n = 64: 3.9 µs vs 5.8 for the per-SM kernel).
+// 1080p, 100 chained steps, µs per step): 8 CTAs per window win for a handful of windows (n = 1 … 9: 2.2-2.3 vs 2.5 with
+// 4 CTAs; from n = 16 clusters of 8 no longer pack the GPCs one CTA per SM: 3.2 vs 2.55), 4 CTAs up to n = 32-33
+// (2.56; at n = 37 = #SMs/4 the clusters of 4 do not all fit one per SM either: 4.0 vs 3.85 with 2 CTAs), 2 CTAs up to
+// #SMs/2 (n = 64 … 74: 3.84 vs 5.75 for the per-SM kernel).
 static int cluster_size_for(const WinArgs &a, const Cfg &cfg, int n)
 {
     if (cfg.cluster == 1) return 1;
@@ -1227,7 +1214,7 @@ static int cluster_size_for(const WinArgs &a, const Cfg &cfg, int n)
         return 1;
     }
     if (16 * n <= sms) return 8;
-    if (4 * n <= sms) return 4;
+    if (4 * n <= sms - 16) return 4;
     if (2 * n <= sms) return 2;
     return 1;
 }

@@ -34,9 +34,11 @@ def main():
     t_local = 1.0 + ranks.rank                      # pretend device time of this rank
     t_max = ranks.max_over_ranks(t_local)
     n_sum = ranks.sum_over_ranks(float(len(mine)))
+    per_rank = ranks.gather(t_local)                # per-rank times in rank order (reported beside the max)
     ranks.barrier()
     with open(os.path.join(out_dir, f"rank{ranks.rank}.json"), "w") as fh:
-        json.dump({"rank": ranks.rank, "world": ranks.world, "mine": mine, "res": res, "t_max": t_max, "n_sum": n_sum}, fh)
+        json.dump({"rank": ranks.rank, "world": ranks.world, "mine": mine, "res": res, "t_max": t_max, "n_sum": n_sum,
+                   "per_rank": per_rank}, fh)
     ranks.close()
 
 

@@ -32,6 +32,7 @@ def test_two_rank_gloo_sharding_and_reductions(tmp_path, oracle):
     # max over ranks of the per-rank time; sum of per-rank unit counts
     assert outs[0]["t_max"] == outs[1]["t_max"] == 2.0
     assert outs[0]["n_sum"] == outs[1]["n_sum"] == 6.0
+    assert outs[0]["per_rank"] == outs[1]["per_rank"] == [1.0, 2.0]
     # every shard tracked its own videos correctly (found the disk centre)
     merged = {}
     for o in outs:
@@ -49,6 +50,9 @@ def test_shard_plan_properties():
         for rank in range(world):
             seen += bench.shard_videos(256, world, rank)
         assert sorted(seen) == list(range(256))
+    # strong scaling = BASELINE configs[2] as written: 256 videos in total → 256 / world per rank
+    assert [len(bench.shard_videos(256, 8, r)) for r in range(8)] == [32] * 8
+    assert bench.workload_config("strong", 8)["videos_per_gpu"] == 32 and bench.workload_config("weak", 8)["videos_per_gpu"] == 256
     a = bench.algorithmic_per_window()
     # tw=25 / 45x45 → 0.9009 M MAC, 1.804 MFLOP, 11,897 B (u8 frames)
     assert a["mac"] == 900900 and a["flops"] == 1803825 and a["bytes"] == 11897

@@ -133,17 +133,17 @@ def test_cluster_kernel_f32_and_unaligned_frames(gpu_pkg, oracle, synth, C):
 
 
 def test_cluster_size_policy(gpu_pkg):
-    """Auto policy: 8 CTAs per window up to #SMs/16 windows, 4 up to #SMs/4, 2 up to #SMs/2, then the per-SM kernels."""
+    """Auto policy: 8 CTAs per window up to #SMs/16 windows, 4 up to (#SMs-16)/4, 2 up to #SMs/2, then the per-SM kernels."""
     import torch
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     H, W, T = 64, 64, 2
-    for n in (1, sms // 16, sms // 16 + 1, sms // 4, sms // 4 + 1, sms // 2, sms // 2 + 1, sms):
+    for n in (1, sms // 16, sms // 16 + 1, (sms - 16) // 4, (sms - 16) // 4 + 1, sms // 2, sms // 2 + 1, sms):
         dev = torch.full((T, n, H, W), 128, dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
         with gpu_pkg.TrackerBatch(n, (H, W), 25, (45, 45), True) as b:
             b.set_fill(128); b.set_guess(np.tile([32, 32], (n, 1)))
             b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
-            want = ("dog_window45_cluster<8>" if 16 * n <= sms else "dog_window45_cluster<4>" if 4 * n <= sms else
+            want = ("dog_window45_cluster<8>" if 16 * n <= sms else "dog_window45_cluster<4>" if 4 * n <= sms - 16 else
                     "dog_window45_cluster<2>" if 2 * n <= sms else "dog_window45_argmax")
             assert b.last_kernel == want, (n, b.last_kernel)
 
