@@ -580,7 +580,8 @@ def run_gpu(args, ranks):
             self.value = v
     tf = _V(benchlib.fp32_peak(dev_index, 0, 5))
     tf2 = _V(benchlib.fp32_peak(dev_index, 1, 5))
-    fp32_peak = max(tf.value, tf2.value)
+    tadd2 = benchlib.fp32_peak(dev_index, 2, 3)      # packed add.rn.f32x2, tera lane-adds/s (half the FFMA lane rate: a
+    fp32_peak = max(tf.value, tf2.value)             # packed add holds the pipe two cycles — no cheaper than two FADDs)
     if balanced:
         balanced["frac_fp32"] = balanced["achieved_tflops"] / fp32_peak
     mode_fill["frac_hbm"] = mode_fill["gb_per_s"] / hbm_peak
@@ -592,19 +593,21 @@ def run_gpu(args, ranks):
     ach_tflops = flops_launch / launch_s / 1e12
     ach_gbs = bytes_launch / launch_s / 1e9
     t_roof = max(flops_launch / (fp32_peak * 1e12), bytes_launch / (hbm_peak * 1e9))
-    # DRAM traffic of this kernel from profiles/r01_window45_rot_ncu_full_selected.csv (one `ncu --set full`
-    # capture of a 20-step launch: dram read 209.1 MB + write 4.4 MB): 10.67 MB per 256-video step
-    traffic_per_step = 10.67e6 if batch_kernel in ("dog_window45_argmax", "dog_window45_rot") else None
+    # DRAM traffic of this kernel from profiles/r02_rot_ncu_full_selected.csv (one `ncu --set full` capture of the
+    # timed 20-step launch: dram read 209.09 MB + write 7.12 MB): 10.81 MB per 256-video step; scaled by the videos
+    # of this rank for the strong-scaling arm (the cluster kernel's own capture: profiles/r02_cluster_…csv)
+    traffic_per_step = 10.81e6 * n / 256 if batch_kernel.startswith("dog_window45") else None
     roofline = {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach_tflops / fp32_peak,
                 "traffic": traffic_per_step * steps_per_launch if traffic_per_step else None,
                 "traffic_note": "dram__bytes_read+write per launch scaled from the ncu --set full capture in profiles/ "
-                                "(10.67 MB per 256-video step vs 3.05 MB algorithmic: 109-byte rows inside 128-byte "
+                                "(10.81 MB per 256-video step vs 3.05 MB algorithmic: 109-byte rows inside 128-byte "
                                 "lines, plus the deliberate L2 prefetch of the 153-row region the next step can touch; "
                                 "DRAM is at 4 % of its peak)",
                 "kernel": batch_kernel,
                 "peak_source": "measured in this run (ptb_measure_fp32_peak of libpawsome_bench.so: dependent FFMA chains, best of 5; "
                                f"scalar {tf.value:.1f}, f32x2 {tf2.value:.1f} TFLOP/s); nominal {NOMINAL_FP32_TFLOPS:.1f}",
+                "packed_add_tera_lane_adds_per_s": tadd2,
                 "launches_in_timed_region": int(timed_launches), "steps_per_launch": steps_per_launch,
                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": bytes_launch,
                 "algorithmic_flops_per_window": alg["flops"], "algorithmic_bytes_per_window": alg["bytes"],
