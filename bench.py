@@ -390,14 +390,19 @@ def run_gpu(args, ranks):
     ext = torch.cuda.ExternalStream(batch.stream, device=device)
     step_stride, frame_stride = n * H * W, H * W
 
-    def run_chain(first_slot, nsteps):
-        """nsteps chained launches starting at ring slot first_slot (wraps at the ring end)."""
-        done = 0
+    def chain_segments(first_slot, nsteps):
+        """(device pointer, steps) of the chained launches covering nsteps from ring slot first_slot (wraps at the ring end)."""
+        segs, done = [], 0
         while done < nsteps:
             s = (first_slot + done) % slots
             m = min(nsteps - done, slots - s)
-            batch.track_device_async(ring.data_ptr() + s * step_stride, step_stride, frame_stride, W, m)
+            segs.append((ring.data_ptr() + s * step_stride, m))
             done += m
+        return segs
+
+    def run_chain(first_slot, nsteps):
+        for ptr, m in chain_segments(first_slot, nsteps):
+            batch.track_device_async(ptr, step_stride, frame_stride, W, m)
 
     # correctness of exactly what is timed: W+K chained steps from slot 0
     batch.set_guess(pos[0])
@@ -429,17 +434,16 @@ def run_gpu(args, ranks):
             run_chain(0, Wm)                                                         # warm-up steps (untimed)
             ranks.barrier()
             torch.cuda.synchronize(device)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             lc0 = batch.launch_count
-            with torch.cuda.stream(ext):
-                e0.record()
-                run_chain(Wm % slots, K)                                             # EXACTLY K timed steps
-                e1.record()
+            # EXACTLY K timed steps: CUDA event, the chained launch(es), CUDA event on the batch's stream, issued back
+            # to back from C (ptb_time_chain) so that no interpreter time sits between the first event and the launch
+            ms_rep = benchlib.time_chain(pkg.lib, batch, chain_segments(Wm % slots, K), step_stride, frame_stride, W,
+                                         batch.stream)
             timed_launches = batch.launch_count - lc0
             batch_kernel = batch.last_kernel or batch_kernel
             torch.cuda.synchronize(device)
             ranks.barrier()
-            reps_local.append(e0.elapsed_time(e1))
+            reps_local.append(ms_rep)
             reps_ms.append(ranks.max_over_ranks(reps_local[-1], device))             # max over ranks, device time
             rep += 1
             if rep >= args.repeats or (rep >= 5 and time.perf_counter() - t_wall0 > 2.5):
@@ -465,12 +469,8 @@ def run_gpu(args, ranks):
         exts = torch.cuda.ExternalStream(bs.stream, device=device)
 
         def chain_s(first_slot, nsteps):
-            done = 0
-            while done < nsteps:
-                sl = (first_slot + done) % slots
-                m2 = min(nsteps - done, slots - sl)
-                bs.track_device_async(ring.data_ptr() + sl * step_stride, step_stride, frame_stride, W, m2)
-                done += m2
+            for ptr, m2 in chain_segments(first_slot, nsteps):
+                bs.track_device_async(ptr, step_stride, frame_stride, W, m2)
 
         bs.set_guess(pos[0][:ns])
         chk_s, _ = bs.track_device(ring.data_ptr(), step_stride, frame_stride, W, min(Wm + K, slots))
@@ -482,14 +482,10 @@ def run_gpu(args, ranks):
             chain_s(0, Wm)
             ranks.barrier()
             torch.cuda.synchronize(device)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(exts):
-                e0.record()
-                chain_s(Wm % slots, K)
-                e1.record()
+            ms_rep = benchlib.time_chain(pkg.lib, bs, chain_segments(Wm % slots, K), step_stride, frame_stride, W, bs.stream)
             torch.cuda.synchronize(device)
             ranks.barrier()
-            loc_s.append(e0.elapsed_time(e1))
+            loc_s.append(ms_rep)
             ms_s.append(ranks.max_over_ranks(loc_s[-1], device))
         kern_s = bs.last_kernel
         bs.close()
@@ -536,13 +532,18 @@ def run_gpu(args, ranks):
         ext2 = torch.cuda.ExternalStream(b2.stream, device=device)
         ss2 = n2 * H * W
 
-        def chain2(first_slot, nsteps):
-            done = 0
+        def segs2(first_slot, nsteps):
+            out, done = [], 0
             while done < nsteps:
                 sl = (first_slot + done) % slots2
                 m2 = min(nsteps - done, slots2 - sl)
-                b2.track_device_async(ring2.data_ptr() + sl * ss2, ss2, H * W, W, m2)
+                out.append((ring2.data_ptr() + sl * ss2, m2))
                 done += m2
+            return out
+
+        def chain2(first_slot, nsteps):
+            for ptr, m2 in segs2(first_slot, nsteps):
+                b2.track_device_async(ptr, ss2, H * W, W, m2)
 
         b2.set_guess(pos2[0])
         chk2, _ = b2.track_device(ring2.data_ptr(), ss2, H * W, W, min(Wm + K, slots2))
@@ -553,13 +554,8 @@ def run_gpu(args, ranks):
             b2.set_guess(pos2[0])
             chain2(0, Wm)
             torch.cuda.synchronize(device)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(ext2):
-                e0.record()
-                chain2(Wm % slots2, K)
-                e1.record()
+            ms2.append(benchlib.time_chain(pkg.lib, b2, segs2(Wm % slots2, K), ss2, H * W, W, b2.stream))
             torch.cuda.synchronize(device)
-            ms2.append(e0.elapsed_time(e1))
         b2.close()
         del ring2
         t2 = float(np.median(ms2)) * 1e-3
@@ -745,7 +741,7 @@ def run_gpu(args, ranks):
                 "config": dict(workload_config(args.scaling, world), repeats=len(reps_ms),
                                l2="inputs larger than L2: each timed step reads a step-slot (531 MB) untouched "
                                   f"since the previous repeat; ring of {slots} slots; L2 flushed between repeats",
-                               timing="CUDA events on the launching stream, median over repeats, max over ranks"),
+                               timing="CUDA events on the launching stream, the event pair and the chained launch issued back to back from C (ptb_time_chain of libpawsome_bench.so), barrier + synchronize on both sides, median over repeats, max over ranks"),
                 "clocks": clocks, "e2e": e2e, "e2e_frames": e2e_frames, "roofline": roofline,
                 "cpu_baseline": cpu, "fullframe_dog": fullframe, "balanced_batch": balanced, "mode_fill": mode_fill,
                 "strong": strong_obj, "ms_K_per_rank": ms_K_per_rank,

@@ -285,7 +285,7 @@ struct pt_batch {
     unsigned long long *d_keys = nullptr;
     unsigned int *d_counters = nullptr;
     unsigned int *d_hist = nullptr;
-    unsigned int *d_xflag = nullptr;     // [n] hand-off flags of the rotating-slot kernel (zero between launches)
+    unsigned int *d_xflag = nullptr;     // [n] hand-off flags + [3] handshake words of the rotating-slot kernel (zero between launches)
     int2 *d_xpos = nullptr;              // [n] hand-off guesses
     int4 *d_pos = nullptr;
     float *d_resp = nullptr;
@@ -643,7 +643,7 @@ int pt_batch_create(int n, int H, int W, double tw, int ws_rows, int ws_cols, in
         const size_t o_cnt = take(sizeof(unsigned int) * 3 * n);                       // [n] completion + [n][2] ticket scratch
         const size_t o_hist = take(sizeof(unsigned int) * pt::kModeScratch * (size_t)n);
         const size_t o_pos = take(sizeof(int4) * n), o_resp = take(sizeof(float) * n);
-        const size_t o_xflag = take(sizeof(unsigned int) * n), o_xpos = take(sizeof(int2) * n);
+        const size_t o_xflag = take(sizeof(unsigned int) * ((size_t)n + 4)), o_xpos = take(sizeof(int2) * n);   // + 3 handshake words
         if (rc == PT_OK && b->d_arena.ensure(off, b) != PT_OK) rc = PT_ERR_CUDA;
         if (rc == PT_OK) {
             char *a0 = (char *)b->d_arena.p;
@@ -1214,7 +1214,7 @@ int pt_batch_set_option(pt_batch *b, const char *name, int value)
     struct Opt { const char *name; int pt::Cfg::* field; int lo, hi; };
     static const Opt opts[] = {
         {"window45", &pt::Cfg::window45, 0, 1},       {"rect45", &pt::Cfg::rect45, 0, 1},
-        {"rot", &pt::Cfg::rot, 0, 2},                 {"skew", &pt::Cfg::skew, 0, 2},
+        {"rot", &pt::Cfg::rot, 0, 3},                 {"skew", &pt::Cfg::skew, 0, 2},
         {"r45_chunks", &pt::Cfg::r45_chunks, 0, 1 << 20}, {"generic_target", &pt::Cfg::generic_target, 1, 1 << 20},
         {"mode_slow", &pt::Cfg::mode_slow, 0, 1},     {"zero_copy", &pt::Cfg::zero_copy, 0, 1},
         {"host_lanes", &pt::Cfg::host_lanes, 0, 1024}, {"cluster", &pt::Cfg::cluster, 0, 8},

@@ -202,6 +202,30 @@ PTB_API int ptb_probe_ffma2_issue(int device, int na, double *ms_out)
     return 0;
 }
 
+// CUDA-event time of a chain of pt_batch_track_device_async calls, events and launches issued back to back from C.
+PTB_API int ptb_time_chain(void *track_fn, void *batch, int nseg, const void *const *bases, const int *Ts,
+                           size_t step_stride, size_t frame_stride, size_t pitch, void *stream, double *ms_out)
+{
+    typedef int (*track_fn_t)(void *, const void *, size_t, size_t, size_t, int, void *);
+    if (!track_fn || !batch || !bases || !Ts || !ms_out || nseg < 1) return -1;
+    track_fn_t fn = (track_fn_t)track_fn;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -2;
+    int rc = 0;
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < nseg && rc == 0; ++i) rc = fn(batch, bases[i], step_stride, frame_stride, pitch, Ts[i], stream);
+    cudaEventRecord(e1, s);
+    const cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return -2;
+    *ms_out = (double)ms;
+    return 0;
+}
+
 // Overwrites `bytes` of scratch on `stream` so nothing useful stays in L2.
 PTB_API int ptb_flush_l2(void *scratch, size_t bytes, void *stream)
 {

@@ -87,6 +87,13 @@ struct Args45 {
     int4 *out_pos; float *out_resp;     // [n] last step
     int2 *next_guess;                   // [n] or null
     int4 *traj_pos; float *traj_resp;   // [T][n] or null
+    // geometry inside the 45×45 / l = 65 frame of the kernels (any window ≤ 45×45 and kernel length ≤ 65: the taps
+    // are zero-padded to 65, outputs beyond wr × wc are masked): radii, output rows / columns, the footprint rows
+    // [f_lo, f_lo + nfr) whose taps are not all zero, groups of 5 output columns, reciprocal of nfr (item → group by
+    // one multiplication: (item · inv_nfr) >> 18), lane stride of a row group in the column pass
+    int rr, rc, wr, wc;
+    int f_lo, nfr, ng, cs;
+    unsigned int inv_nfr;
     int skew;                           // 1: alternate the row passes of the two windows of a CTA (token); 2: lock
     int tm_rows_step, tm_rows_frame;    // dog_window45_cluster, TMA tensor mode: rows of the 2-D frame tensor per step / per video
     unsigned int *xflag;                // [n] hand-off flags of dog_window45_rot (zero between launches)
@@ -145,9 +152,10 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 // f32 frames: lane = column (+32q), coalesced 4-byte loads.
 // kContig: warp w takes the contiguous rows [w·RPW, (w+1)·RPW) instead of w, w+8, … (the cluster kernel row-filters
 // the rows a warp staged without a CTA barrier in between).
+// Only rows [f_lo, f_hi) are staged (the per-window kernels skip footprint rows whose taps are all zero).
 template <int NROWS, int FCOLS = FC, int PITCH = PIN, bool kContig = false>
 __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H, int W, int fy0, int fx0,
-                                           float fill, float *s_in, int warp, int lane)
+                                           float fill, float *s_in, int warp, int lane, int f_lo = 0, int f_hi = NROWS)
 {
     constexpr int RPW = (NROWS + NWARPS - 1) / NWARPS;   // 14 rows per warp for a footprint (last ones masked)
     constexpr int NQ = (FCOLS + 31) / 32;
@@ -156,7 +164,7 @@ __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H,
     for (int r = 0; r < RPW; ++r) {
         const int f = kContig ? warp * RPW + r : warp + r * NWARPS;
         const int Y = fy0 + f;
-        const bool yok = (f < NROWS) && (Y >= 0) && (Y < H);
+        const bool yok = (f < NROWS) && (f >= f_lo) && (f < f_hi) && (Y >= 0) && (Y < H);
         const float *rowp = frame + (size_t)(yok ? Y : 0) * pitch;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -171,7 +179,7 @@ __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H,
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int c = lane + 32 * q;
-            if (f < NROWS && c < FCOLS) s_in[f * PITCH + c] = px[r][q] - fill;
+            if (f < NROWS && f >= f_lo && f < f_hi && c < FCOLS) s_in[f * PITCH + c] = px[r][q] - fill;
         }
     }
 }
@@ -185,7 +193,7 @@ __device__ __forceinline__ void stage_rows(const float *frame, int pitch, int H,
 // pitch ≥ round_up(W, 4) (checked by window45_supported).
 template <int NROWS, bool kInterior, int FCOLS = FC, int PITCH = PIN, bool kContig = false>
 __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
-                                              float fill, float *s_in, int warp, int lane)
+                                              float fill, float *s_in, int warp, int lane, int f_lo = 0, int f_hi = NROWS)
 {
     constexpr int RPW = (NROWS + NWARPS - 1) / NWARPS;
     const int xa = fx0 & ~3, phase = fx0 - xa;             // aligned start, phase 0..3
@@ -216,7 +224,7 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
     for (int r = 0; r < RPW; ++r) {
         const int f = kContig ? warp * RPW + r : warp + r * NWARPS;
         const int Y = fy0 + f;
-        const bool ok = wordok && (f < NROWS) && (kInterior || ((Y >= 0) && (Y < H)));
+        const bool ok = wordok && (f < NROWS) && (f >= f_lo) && (f < f_hi) && (kInterior || ((Y >= 0) && (Y < H)));
         wd[r] = fillw;
         if (ok) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(wd[r]) : "l"(addr));
         addr += rstep;                                       // one 64-bit add per load
@@ -226,7 +234,7 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int f = kContig ? warp * RPW + r : warp + r * NWARPS;
-        if (f < NROWS) {
+        if (f < NROWS && f >= f_lo && f < f_hi) {
             unsigned int w = kInterior ? wd[r] : ((wd[r] & keep) | (fillw & ~keep));
             w = __funnelshift_r(w, w, 8 * rot);            // byte k of w = pixel (k + rot) & 3 of the word
             float *dst = s_in + f * PITCH;
@@ -241,20 +249,20 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
 
 template <int NROWS, int FCOLS = FC, int PITCH = PIN, bool kContig = false>
 __device__ __forceinline__ void stage_rows(const uint8_t *frame, int pitch, int H, int W, int fy0, int fx0,
-                                           float fill, float *s_in, int warp, int lane)
+                                           float fill, float *s_in, int warp, int lane, int f_lo = 0, int f_hi = NROWS)
 {
     // interior: every aligned word the rows touch lies inside the frame → no byte masks, no row checks
     constexpr int NWORDS = (FCOLS + 3 + 3) / 4;               // aligned words covering FCOLS columns at any phase (28 for 109)
-    const bool interior = (fy0 >= 0) && (fy0 + NROWS <= H) && ((fx0 & ~3) >= 0) && ((fx0 & ~3) + 4 * NWORDS <= W);
-    if (interior) stage_rows_u8<NROWS, true, FCOLS, PITCH, kContig>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
-    else stage_rows_u8<NROWS, false, FCOLS, PITCH, kContig>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    const bool interior = (fy0 + f_lo >= 0) && (fy0 + f_hi <= H) && ((fx0 & ~3) >= 0) && ((fx0 & ~3) + 4 * NWORDS <= W);
+    if (interior) stage_rows_u8<NROWS, true, FCOLS, PITCH, kContig>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane, f_lo, f_hi);
+    else stage_rows_u8<NROWS, false, FCOLS, PITCH, kContig>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane, f_lo, f_hi);
 }
 
 template <typename PixT>
 __device__ __forceinline__ void stage_tile(const PixT *frame, int pitch, int H, int W, int fy0, int fx0,
-                                           float fill, float *s_in, int warp, int lane)
+                                           float fill, float *s_in, int warp, int lane, int f_lo, int f_hi)
 {
-    stage_rows<FR>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane);
+    stage_rows<FR>(frame, pitch, H, W, fy0, fx0, fill, s_in, warp, lane, f_lo, f_hi);
 }
 
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -344,30 +352,46 @@ __device__ __forceinline__ void convert_rows_u8(const uint8_t *raw, int raw_y0, 
 // ---- row pass over one staged 109×109 tile: item = (footprint row f, group gq of 5 output columns);
 // lanes walk rows.  One FADD (symmetric fold) feeds one packed FFMA2 advancing (narrow, wide).
 // NROWS rows of s_in (from row 0) → NROWS rows of s_mid (from the pointer given).
+__device__ __forceinline__ void row_item45(const float *row, float2 *dst, const Taps45 &tp)
+{
+    float x[RR + 2 * HW];
+#pragma unroll
+    for (int i = 0; i < RR + 2 * HW; ++i) x[i] = row[i];
+    float2 acc[RR];                                  // (narrow, wide) per output
+#pragma unroll
+    for (int j = 0; j < RR; ++j) acc[j] = fmul2(make_float2(x[j + HW], x[j + HW]), tp.rt[0]);
+#pragma unroll
+    for (int d = 1; d <= HW; ++d) {
+#pragma unroll
+        for (int j = 0; j < RR; ++j) {
+            const float s = x[j + HW - d] + x[j + HW + d];   // exact for u8 frames (integers)
+            acc[j] = ffma2(make_float2(s, s), tp.rt[d], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RR; ++j) dst[j] = acc[j];
+}
+
 template <int NROWS = FR>
 __device__ __forceinline__ void row_pass45(const float *s_in, float2 *s_mid, int tid, const Taps45 &tp)
 {
 #pragma unroll 1
     for (int item = tid; item < NROWS * (WC / RR); item += THREADS) {
         const int gq = item / NROWS, f = item - gq * NROWS;
-        const float *row = s_in + f * PIN + gq * RR;
-        float x[RR + 2 * HW];
-#pragma unroll
-        for (int i = 0; i < RR + 2 * HW; ++i) x[i] = row[i];
-        float2 acc[RR];                                  // (narrow, wide) per output
-#pragma unroll
-        for (int j = 0; j < RR; ++j) acc[j] = fmul2(make_float2(x[j + HW], x[j + HW]), tp.rt[0]);
-#pragma unroll
-        for (int d = 1; d <= HW; ++d) {
-#pragma unroll
-            for (int j = 0; j < RR; ++j) {
-                const float s = x[j + HW - d] + x[j + HW + d];   // exact for u8 frames (integers)
-                acc[j] = ffma2(make_float2(s, s), tp.rt[d], acc[j]);
-            }
-        }
-        float2 *dst = s_mid + f * PM + gq * RR;
-#pragma unroll
-        for (int j = 0; j < RR; ++j) dst[j] = acc[j];
+        row_item45(s_in + f * PIN + gq * RR, s_mid + f * PM + gq * RR, tp);
+    }
+}
+
+// The same over the footprint rows [f_lo, f_lo + nfr) and the first ng column groups only (windows smaller than
+// 45×45 / kernels shorter than 65: the other rows meet zero taps only, the other columns are masked).
+__device__ __forceinline__ void row_pass45_rt(const float *s_in, float2 *s_mid, int tid, const Taps45 &tp,
+                                              int f_lo, int nfr, int ng, unsigned int inv_nfr)
+{
+    const int nitems = nfr * ng;
+#pragma unroll 1
+    for (int item = tid; item < nitems; item += THREADS) {
+        const int gq = (int)(((unsigned int)item * inv_nfr) >> 18), f = f_lo + item - gq * nfr;
+        row_item45(s_in + f * PIN + gq * RR, s_mid + f * PM + gq * RR, tp);
     }
 }
 
@@ -377,10 +401,13 @@ __device__ __forceinline__ void row_pass45(const float *s_in, float2 *s_mid, int
 // output rectangle of wr_tot × wc_tot: outputs beyond it are masked, the key carries the rectangle's
 // column-major index.  map_out (optional) receives the responses, row-major with pitch wc_tot.
 __device__ __forceinline__ unsigned long long col_pass45(const float2 *s_mid, int tid, const Taps45 &tp,
-                                                         int gy0, int gx0, int wr_tot, int wc_tot, float *map_out)
+                                                         int gy0, int gx0, int wr_tot, int wc_tot, float *map_out, int cs = 48)
 {
-    if (tid >= COL_ITEMS) return 0ull;
-    const int h = tid / WC, xq = tid - h * WC;
+    // items are laid out cs = 48 (32, 16 for narrow windows) per row group: a half-warp — the unit of a 64-bit
+    // shared-memory access — never straddles two row groups, whose addresses differ by an odd multiple of the pitch
+    // (30 % excess wavefronts before); lanes and row groups beyond the rectangle leave at once
+    const int h = cs == 48 ? tid / 48 : (tid >> (cs == 32 ? 5 : 4)), xq = tid - h * cs;
+    if (h >= NG || xq >= WC || gx0 + xq >= wc_tot || gy0 + h * R >= wr_tot) return 0ull;
     const float2 *col = s_mid + (h * R) * PM + xq;
     float2 accP[R / 2], accM[R / 2];
     float acc8p = 0.f, acc8m = 0.f;
@@ -410,7 +437,6 @@ __device__ __forceinline__ unsigned long long col_pass45(const float2 *s_mid, in
     for (int p = 0; p < R / 2; ++p) { acc[2 * p] = accP[p].x + accM[p].x; acc[2 * p + 1] = accP[p].y + accM[p].y; }
     acc[R - 1] = acc8p + acc8m;
     const int gx = gx0 + xq, gyb = gy0 + h * R;
-    if (gx >= wc_tot || gyb >= wr_tot) return 0ull;
     float bv = acc[0] + 0.0f;
     int bj = 0;
 #pragma unroll
@@ -431,10 +457,14 @@ __device__ __forceinline__ void bar_half(int half)
     asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(THREADS) : "memory");
 }
 
-template <typename PixT>
+// kFull: the default geometry (l = 65, 45×45 window) with every bound a compile-time constant; !kFull: any shorter
+// kernel / smaller window, bounds from Args45 (see there).
+template <typename PixT, bool kFull>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Taps45 tp)
 {
+    const int g_rr = kFull ? WR / 2 : a.rr, g_rc = kFull ? WC / 2 : a.rc, g_wr = kFull ? WR : a.wr, g_wc = kFull ? WC : a.wc;
+    const int g_flo = kFull ? 0 : a.f_lo, g_nfr = kFull ? FR : a.nfr, g_cs = kFull ? 48 : a.cs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_keys[2][2 * NWARPS];
 
@@ -464,6 +494,9 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
     const bool locked = a.skew == 2 && NB > 0;     // row passes mutually exclusive through a lock in shared memory
     __shared__ int s_rowlock;
     if (threadIdx.x == 0) s_rowlock = 0;
+    // reduced geometry: footprint rows outside [f_lo, f_lo + nfr) are never written; the column pass still reads
+    // them (against zero taps), so they must hold finite values
+    if (!kFull && a.nfr < FR) for (int i = tid; i < (int)(HALF_SMEM / 16); i += THREADS) reinterpret_cast<float4 *>(s_in)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     int round = 0;
 
@@ -477,13 +510,13 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         const PixT *frame = a.frame_ptrs
             ? reinterpret_cast<const PixT *>(a.frame_ptrs[(size_t)t * a.n + v])
             : reinterpret_cast<const PixT *>(a.frames) + (size_t)t * a.step_stride + (size_t)v * a.frame_stride;
-        const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);   // window origin, 0-based
-        const int fy0 = wy0 - HW, fx0 = wx0 - HW;                        // footprint origin
+        const int wy0 = g.x - 1 - g_rr, wx0 = g.y - 1 - g_rc;           // window origin, 0-based
+        const int fy0 = wy0 - HW, fx0 = wx0 - HW;                        // footprint origin (of the l = 65 frame)
 
         // (Fetching the footprint rows of zero-copy HOST frames with one cp.async.bulk per row instead of these lane
         // loads was measured and dropped: NVML counted 11.4 MB of PCIe reads per 256-window step instead of 5.8 MB,
         // the link saturated at 61 GB/s and the step took 147 µs instead of 111 µs.)
-        stage_tile<PixT>(frame, a.pitch, a.H, a.W, fy0, fx0, fill, s_in, warp, lane);
+        stage_tile<PixT>(frame, a.pitch, a.H, a.W, fy0, fx0, fill, s_in, warp, lane, g_flo, g_flo + g_nfr);
 
         // ---- warm L2 with everything the NEXT step can touch: its window centre is inside this
         // step's window, so its footprint lies within ±22 px of this one (153 rows × ≤3 lines).
@@ -516,7 +549,8 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             else           { if (round < NA) asm volatile("bar.sync 3, %0;" ::"n"(CTA_THREADS) : "memory"); }
         }
 
-        row_pass45(s_in, s_mid, tid, tp);
+        if (kFull) row_pass45<FR>(s_in, s_mid, tid, tp);
+        else row_pass45_rt(s_in, s_mid, tid, tp, a.f_lo, a.nfr, a.ng, a.inv_nfr);
         bar_half(half);
         if (locked && tid == 0) atomicExch(&s_rowlock, 0);
         if (tokens) {                                          // hand the row-pass token to the other window
@@ -526,7 +560,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         ++round;
         PT_PROBE(3, tid);
 
-        const unsigned long long key = warp_max_key(col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr));
+        const unsigned long long key = warp_max_key(col_pass45(s_mid, tid, tp, 0, 0, g_wr, g_wc, nullptr, g_cs));
         if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
         bar_half(half);
         PT_PROBE(4, tid);
@@ -535,7 +569,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
             // s_key is double-buffered by iteration parity
             const unsigned long long k = warp_max_key(s_key[(it & 1) * NWARPS + (lane & (NWARPS - 1))]);
             const unsigned int idx = key_index(k);
-            const int xx = (int)(idx / WR), yy = (int)(idx - xx * WR);
+            const int xx = (int)(idx / (unsigned int)g_wr), yy = (int)(idx - xx * g_wr);
             const int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;                   // absolute index (:60)
             const int ci = min(max(raw_i, 1), a.H), cj = min(max(raw_j, 1), a.W);   // clamp (:61)
             if (tid == 0) {
@@ -568,7 +602,14 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
 // release flag; the receiving slot is empty and polls), nh of n windows per step; the L2 prefetch issued by the
 // old SM serves the new one (L2 is shared).  The row passes of the two halves of an SM exclude each other
 // through a lock in shared memory (same effect as the token of dog_window45_argmax, but a half never waits for
-// a partner that is empty or late).  All CTAs must be co-resident (cooperative launch).
+// a partner that is empty or late).  Hopping needs all CTAs co-resident.  Instead of a cooperative launch (which
+// serialises against every other kernel on the device and cannot share it) the kernel is launched plainly and the
+// CTAs agree on the schedule themselves: every CTA counts itself in (xsync[0]); the CTA that completes the count
+// proposes "rotate" (all CTAs are resident and stay so until they have run their steps), a CTA that has waited ≈ 30 µs
+// without seeing a decision proposes "static"; the first proposal wins (one atomicCAS on xsync[1]) and every CTA
+// follows it.  "Static" is the same schedule with the empty slots standing still (nh = 0 hops: window σ stays in
+// slot σ), i.e. the split of dog_window45_argmax, which needs no co-residency.  The last CTA to leave zeroes the
+// three words.  (Measured: same launch time as the cooperative launch, 184 µs per 20 steps.)
 // ---------------------------------------------------------------------------------------------------
 // window held by slot `slot` of a ring of R slots at step t (m windows, nh = R − m empty slots), or −1
 __device__ __forceinline__ int rot_window(int slot, int t, int R, int m, int nh)
@@ -592,10 +633,12 @@ __device__ __forceinline__ int rot_window_rem(int slot, int remR, int remM, int 
     return u;
 }
 
-template <typename PixT>
+template <typename PixT, bool kFull>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps45 tp)
 {
+    const int g_rr = kFull ? WR / 2 : a.rr, g_rc = kFull ? WC / 2 : a.rc, g_wr = kFull ? WR : a.wr, g_wc = kFull ? WC : a.wc;
+    const int g_flo = kFull ? 0 : a.f_lo, g_nfr = kFull ? FR : a.nfr, g_cs = kFull ? 48 : a.cs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_keys[2][2 * NWARPS];
     __shared__ int s_rowlock;
@@ -608,9 +651,24 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
     float *s_in = reinterpret_cast<float *>(smem_raw + half * HALF_SMEM);
     float2 *s_mid = reinterpret_cast<float2 *>(s_in + FR * PIN + 1);
     unsigned long long *s_key = s_keys[half];
-    const int R = 2 * (int)gridDim.x, m = a.n, nh = R - m, slot = (int)blockIdx.x + (int)gridDim.x * half;
-    if (threadIdx.x == 0) s_rowlock = 0;
+    const int R = 2 * (int)gridDim.x, m = a.n, slot = (int)blockIdx.x + (int)gridDim.x * half;
+    __shared__ unsigned int s_mode;
+    if (threadIdx.x == 0) {
+        s_rowlock = 0;
+        unsigned int *xs = a.xflag + a.n;                  // [0] arrived, [1] decision (1 rotate, 2 static), [2] left
+        unsigned int mode;
+        if (atomicAdd(xs, 1u) + 1u == gridDim.x) atomicCAS(xs + 1, 0u, 1u);
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(mode) : "l"(xs + 1) : "memory");
+            if (mode) break;
+            if (a.skew < 0 || clock64() - t0 > (1ll << 16)) atomicCAS(xs + 1, 0u, 2u);   // (skew < 0: option rot = 3, tests)
+        }
+        s_mode = mode;
+    }
+    if (!kFull && a.nfr < FR) for (int i = tid; i < (int)(HALF_SMEM / 16); i += THREADS) reinterpret_cast<float4 *>(s_in)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
+    const int nh = (s_mode == 1u) ? R - m : 0;           // static: the empty slots do not move, nobody hops
 
     int prev_v = -1;
     int2 g = make_int2(0, 0);
@@ -650,10 +708,10 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
         }
         PT_PROBE_BEGIN(a, v, t, tid)
         const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)t * a.step_stride + (size_t)v * a.frame_stride;
-        const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);
+        const int wy0 = g.x - 1 - g_rr, wx0 = g.y - 1 - g_rc;
         const int fy0 = wy0 - HW, fx0 = wx0 - HW;
 
-        stage_tile<PixT>(frame, a.pitch, a.H, a.W, fy0, fx0, fill, s_in, warp, lane);
+        stage_tile<PixT>(frame, a.pitch, a.H, a.W, fy0, fx0, fill, s_in, warp, lane, g_flo, g_flo + g_nfr);
 
         if (t + 1 < a.T) {                                       // warm L2 with everything the next step can touch
             const PixT *nframe = frame + a.step_stride;
@@ -680,12 +738,13 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
         bar_half(half);
         PT_PROBE(2, tid);
 
-        row_pass45(s_in, s_mid, tid, tp);
+        if (kFull) row_pass45<FR>(s_in, s_mid, tid, tp);
+        else row_pass45_rt(s_in, s_mid, tid, tp, a.f_lo, a.nfr, a.ng, a.inv_nfr);
         bar_half(half);
         if (tid == 0) atomicExch(&s_rowlock, 0);
         PT_PROBE(3, tid);
 
-        const unsigned long long key = warp_max_key(col_pass45(s_mid, tid, tp, 0, 0, WR, WC, nullptr));
+        const unsigned long long key = warp_max_key(col_pass45(s_mid, tid, tp, 0, 0, g_wr, g_wc, nullptr, g_cs));
         if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
         bar_half(half);
         PT_PROBE(4, tid);
@@ -694,7 +753,7 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
             // s_key is double-buffered by iteration parity
             const unsigned long long k = warp_max_key(s_key[(it & 1) * NWARPS + (lane & (NWARPS - 1))]);
             const unsigned int idx = key_index(k);
-            const int xx = (int)(idx / WR), yy = (int)(idx - xx * WR);
+            const int xx = (int)(idx / (unsigned int)g_wr), yy = (int)(idx - xx * g_wr);
             const int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;
             const int ci = min(max(raw_i, 1), a.H), cj = min(max(raw_j, 1), a.W);
             if (tid == 0) {
@@ -714,6 +773,12 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
             }
             g = make_int2(ci, cj);
         }
+    }
+    // the last CTA to leave zeroes the handshake words for the next launch (every CTA has read the decision by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int *xs = a.xflag + a.n;
+        if (atomicAdd(xs + 2, 1u) == gridDim.x - 1u) { xs[0] = 0u; xs[1] = 0u; xs[2] = 0u; }
     }
 }
 
@@ -1048,12 +1113,14 @@ __device__ __forceinline__ unsigned long long col_pass_slice(const float2 *s_mid
     return pack_key(bv, (unsigned int)(gx * wr_tot + gyb + bj));
 }
 
-template <typename PixT, int C>
+template <typename PixT, int C, bool kFull>
 __global__ void __launch_bounds__(CL_THREADS, 2)
 dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ Taps45 tp, const int use_bulk,
                      const __grid_constant__ CUtensorMap tmap)
 {
     using G = SliceGeom<C>;
+    // (kFull: default geometry, compile-time bounds; else a shorter kernel — zero-padded taps — or a smaller window)
+    const int g_rr = kFull ? WR / 2 : a.rr, g_rc = kFull ? WC / 2 : a.rc, g_wr = kFull ? WR : a.wr, g_wc = kFull ? WC : a.wc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_mbar[2];                // arrival of the prefetched regions
     __shared__ __align__(8) unsigned long long s_xbar[2];                // arrival of the argmax candidates (by step parity)
@@ -1062,7 +1129,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_rank();
     const int v = (int)blockIdx.x / C;
-    const int xs = (WC * rank) / C, width = (WC * (rank + 1)) / C - xs;  // this CTA's output columns [xs, xs + width)
+    const int xs = (g_wc * rank) / C, width = (g_wc * (rank + 1)) / C - xs;  // this CTA's output columns [xs, xs + width)
     constexpr bool kU8 = sizeof(PixT) == 1;
     const bool bulk = kU8 && use_bulk != 0;
     unsigned char *rgn = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);      // 128-byte aligned (TMA tile destination)
@@ -1104,7 +1171,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
         }
     };
 
-    if (bulk) issue_region(0, 0, g.x - 1 - (WR / 2) - HW, g.y - 1 - (WC / 2) - HW + xs);
+    if (bulk) issue_region(0, 0, g.x - 1 - g_rr - HW, g.y - 1 - g_rc - HW + xs);
 
     for (int t = 0; t < a.T; ++t) {
         const int par = t & 1;
@@ -1113,7 +1180,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
         if (tid == 0) mbar_arrive_expect_tx(xbar0 + 8u * par, 8u * NWARPS * C);
         const PixT *frame = a.frame_ptrs ? reinterpret_cast<const PixT *>(a.frame_ptrs[(size_t)t * a.n + v])
                                          : frame0 + (size_t)t * a.step_stride;
-        const int wy0 = g.x - 1 - (WR / 2), wx0 = g.y - 1 - (WC / 2);
+        const int wy0 = g.x - 1 - g_rr, wx0 = g.y - 1 - g_rc;
         const int fy0 = wy0 - HW, fxs = wx0 - HW + xs;                       // footprint origin of this slice
         if (bulk) {
             const int xw0 = fxs & ~3;
@@ -1158,7 +1225,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
         __syncthreads();                     // the column pass reads every warp's rows of s_midT
         PT_PROBE(3, tid + rank);
 
-        unsigned long long key = warp_max_key(col_pass_slice<C>(s_midT, tid, tp, width, 0, xs, WR, WC));
+        unsigned long long key = warp_max_key(col_pass_slice<C>(s_midT, tid, tp, width, 0, xs, g_wr, g_wc));
         // Every warp hands its candidate to every CTA of the cluster (its own included) with st.async, which also
         // completes 8 bytes on the receiver's mbarrier; a CTA waits only for ITS 8·C·8 bytes — no cluster-wide
         // rendezvous.  Slots and mbarriers are double-buffered by step parity: a CTA can only send step t+2 after it
@@ -1173,7 +1240,7 @@ dog_window45_cluster(const __grid_constant__ Args45 a, const __grid_constant__ T
             if (NWARPS * C > 32) { const unsigned long long k2 = s_xk[par][32 + lane]; k = k2 > k ? k2 : k; }
             k = warp_max_key(k);
             const unsigned int idx = key_index(k);
-            const int xx = (int)(idx / WR), yy = (int)(idx - xx * WR);
+            const int xx = (int)(idx / (unsigned int)g_wr), yy = (int)(idx - xx * g_wr);
             const int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;                   // absolute index (:60)
             const int ci = min(max(raw_i, 1), a.H), cj = min(max(raw_j, 1), a.W);   // clamp (:61)
             if (tid == 0 && rank == 0) {
@@ -1240,6 +1307,8 @@ static tmap_encode_fn tmap_encoder()
     return fn;
 }
 
+static bool full_geometry(const Args45 &k) { return k.wr == WR && k.wc == WC && k.f_lo == 0 && k.nfr == FR; }
+
 template <typename PixT, int C>
 static cudaError_t launch_cluster_t(Args45 k, const Taps45 &tp, int use_bulk, cudaStream_t s)
 {
@@ -1275,7 +1344,8 @@ static cudaError_t launch_cluster_t(Args45 k, const Taps45 &tp, int use_bulk, cu
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    return cudaLaunchKernelEx(&lc, dog_window45_cluster<PixT, C>, k, tp, use_bulk, tmap);
+    if (full_geometry(k)) return cudaLaunchKernelEx(&lc, dog_window45_cluster<PixT, C, true>, k, tp, use_bulk, tmap);
+    return cudaLaunchKernelEx(&lc, dog_window45_cluster<PixT, C, false>, k, tp, use_bulk, tmap);
 }
 
 static cudaError_t launch_cluster(const Args45 &k, const Taps45 &tp, const Cfg &cfg, int C, int pixel, cudaStream_t s)
@@ -1295,13 +1365,14 @@ static cudaError_t launch_cluster(const Args45 &k, const Taps45 &tp, const Cfg &
     return launch_cluster_t<float, 8>(k, tp, 0, s);
 }
 
-#define PT_CLUSTER_OPTINS                                                            \
-    PT_OPTIN((dog_window45_cluster<uint8_t, 2>), SliceGeom<2>::smem_bytes(true))     \
-    PT_OPTIN((dog_window45_cluster<uint8_t, 4>), SliceGeom<4>::smem_bytes(true))     \
-    PT_OPTIN((dog_window45_cluster<uint8_t, 8>), SliceGeom<8>::smem_bytes(true))     \
-    PT_OPTIN((dog_window45_cluster<float, 2>), SliceGeom<2>::smem_bytes(false))      \
-    PT_OPTIN((dog_window45_cluster<float, 4>), SliceGeom<4>::smem_bytes(false))      \
-    PT_OPTIN((dog_window45_cluster<float, 8>), SliceGeom<8>::smem_bytes(false))
+#define PT_CLUSTER_OPTINS_G(F)                                                          \
+    PT_OPTIN((dog_window45_cluster<uint8_t, 2, F>), SliceGeom<2>::smem_bytes(true))     \
+    PT_OPTIN((dog_window45_cluster<uint8_t, 4, F>), SliceGeom<4>::smem_bytes(true))     \
+    PT_OPTIN((dog_window45_cluster<uint8_t, 8, F>), SliceGeom<8>::smem_bytes(true))     \
+    PT_OPTIN((dog_window45_cluster<float, 2, F>), SliceGeom<2>::smem_bytes(false))      \
+    PT_OPTIN((dog_window45_cluster<float, 4, F>), SliceGeom<4>::smem_bytes(false))      \
+    PT_OPTIN((dog_window45_cluster<float, 8, F>), SliceGeom<8>::smem_bytes(false))
+#define PT_CLUSTER_OPTINS PT_CLUSTER_OPTINS_G(true) PT_CLUSTER_OPTINS_G(false)
 
 // ===================================================================================================
 // host side
@@ -1328,7 +1399,9 @@ void window45_set_debug(long long *dev_buf) { g_dbg = dev_buf; }
 
 bool window45_supported(const WinArgs &a, int pixel)
 {
-    if (!(a.L == L && a.wr == WR && a.wc == WC && !a.rect_mode && a.map_out == nullptr)) return false;
+    // any kernel length up to 65 (zero-padded taps) and any window up to 45×45 (masked outputs, rows and column
+    // groups without work skipped): target_width ≤ 25 with its default window
+    if (!(a.L <= L && a.wr <= WR && a.wc <= WC && !a.rect_mode && a.map_out == nullptr)) return false;
     if (pixel == 0 && a.frame_ptrs) return (a.pitch & 3) == 0 && a.pitch >= ((a.W + 3) & ~3);   // caller checked the pointers
     if (pixel == 0 && a.frames) {
         // the u8 staging path loads aligned 32-bit words
@@ -1343,9 +1416,12 @@ bool window45_supported(const WinArgs &a, int pixel)
 // fold the symmetric row factors (index d = |k − 32|) and pair the column taps.
 static void fold_taps(const WinArgs &a, Taps45 &tp)
 {
-    const float *rp = a.h_taps, *rm = a.h_taps + L, *cp = a.h_taps + 2 * L, *cm = a.h_taps + 3 * L;
-    auto at = [](const float *t, int k) { return (k >= 0 && k < L) ? t[k] : 0.f; };
-    for (int d = 0; d <= HW; ++d) tp.rt[d] = make_float2(rp[HW + d], rm[HW + d]);
+    // a kernel of length a.L ≤ 65 sits centred in the 65 taps of these kernels, zeros around it (adding 0·x changes
+    // no sum)
+    const int off = HW - a.L / 2;
+    const float *rp = a.h_taps, *rm = a.h_taps + a.L, *cp = a.h_taps + 2 * a.L, *cm = a.h_taps + 3 * a.L;
+    auto at = [&](const float *t, int k) { k -= off; return (k >= 0 && k < a.L) ? t[k] : 0.f; };
+    for (int d = 0; d <= HW; ++d) tp.rt[d] = make_float2(at(rp, HW + d), at(rm, HW + d));
     for (int q = 0; q <= L; ++q) {
         tp.cpp[q] = make_float2(at(cp, q), at(cp, q - 1));
         tp.cmq[q] = make_float2(at(cm, q), at(cm, q - 1));
@@ -1361,10 +1437,14 @@ cudaError_t window45_init_device()
 #define PT_OPTIN(k, bytes)                                                                      \
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));       \
     if (e != cudaSuccess) return e;
-    PT_OPTIN(dog_window45_argmax<uint8_t>, smem)
-    PT_OPTIN(dog_window45_argmax<float>, smem)
-    PT_OPTIN(dog_window45_rot<uint8_t>, smem)
-    PT_OPTIN(dog_window45_rot<float>, smem)
+    PT_OPTIN((dog_window45_argmax<uint8_t, true>), smem)
+    PT_OPTIN((dog_window45_argmax<float, true>), smem)
+    PT_OPTIN((dog_window45_rot<uint8_t, true>), smem)
+    PT_OPTIN((dog_window45_rot<float, true>), smem)
+    PT_OPTIN((dog_window45_argmax<uint8_t, false>), smem)
+    PT_OPTIN((dog_window45_argmax<float, false>), smem)
+    PT_OPTIN((dog_window45_rot<uint8_t, false>), smem)
+    PT_OPTIN((dog_window45_rot<float, false>), smem)
     PT_OPTIN(dog_rect45_march<uint8_t>, smem)
     PT_OPTIN(dog_rect45_march<float>, smem)
     PT_CLUSTER_OPTINS
@@ -1409,7 +1489,13 @@ cudaError_t launch_window45(const WinArgs &a, const Cfg &cfg, int n, int pixel, 
 #ifdef PT_PROBES
     k.dbg = g_dbg;
 #endif
-    k.skew = cfg.skew;
+    k.rr = a.rr; k.rc = a.rc; k.wr = a.wr; k.wc = a.wc;
+    k.f_lo = HW - a.L / 2;                                  // first footprint row that meets a non-zero tap
+    k.nfr = a.wr + 2 * (a.L / 2);
+    k.ng = (a.wc + RR - 1) / RR;
+    k.inv_nfr = (1u << 18) / (unsigned int)k.nfr + 1u;      // (item · inv) >> 18 = item / nfr for every item < 9·nfr + 256
+    k.cs = a.wc <= 16 ? 16 : a.wc <= 32 ? 32 : 48;
+    k.skew = cfg.rot == 3 ? -1 : cfg.skew;      // rot = 3: dog_window45_rot's handshake settles on the static schedule at once
     k.tm_rows_step = 0; k.tm_rows_frame = 0;
     k.xflag = a.xflag; k.xpos = a.xpos;
     const int C = cluster_size_for(a, cfg, n);
@@ -1422,19 +1508,25 @@ cudaError_t launch_window45(const WinArgs &a, const Cfg &cfg, int n, int pixel, 
     // one CTA per SM, two windows per CTA; with n ≤ #SMs every window gets its own SM
     const int grid = std::min(sms, n);
     const size_t smem = 2 * HALF_SMEM;
+    const bool full = full_geometry(k);
     if (uses_rot(a, cfg, n)) {
-        void *params[2] = {(void *)&k, (void *)&tp};
-        if (pixel == 0)
-            e = cudaLaunchCooperativeKernel((const void *)dog_window45_rot<uint8_t>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
-        else
-            e = cudaLaunchCooperativeKernel((const void *)dog_window45_rot<float>, dim3(grid), dim3(CTA_THREADS), params, smem, s);
-        if (e == cudaSuccess) return e;
-        // the CTAs cannot all be co-resident right now (device shared with other work): the windows cannot hop
-        // safely — run the static split instead
-        cudaGetLastError();
+        // plain launch: the CTAs establish co-residency themselves and fall back to the static schedule otherwise
+        if (full) {
+            if (pixel == 0) dog_window45_rot<uint8_t, true><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+            else dog_window45_rot<float, true><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        } else {
+            if (pixel == 0) dog_window45_rot<uint8_t, false><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+            else dog_window45_rot<float, false><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        }
+        return cudaGetLastError();
     }
-    if (pixel == 0) dog_window45_argmax<uint8_t><<<grid, CTA_THREADS, smem, s>>>(k, tp);
-    else dog_window45_argmax<float><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+    if (full) {
+        if (pixel == 0) dog_window45_argmax<uint8_t, true><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        else dog_window45_argmax<float, true><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+    } else {
+        if (pixel == 0) dog_window45_argmax<uint8_t, false><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        else dog_window45_argmax<float, false><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+    }
     return cudaGetLastError();
 }
 

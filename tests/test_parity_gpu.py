@@ -622,7 +622,7 @@ def test_batch_sizes_exercise_cta_video_loop(gpu_pkg, oracle, n, T):
 def test_rotating_slots_equal_static_split(gpu_pkg, dtype):
     """dog_window45_rot vs dog_window45_argmax on the same 240-video, 11-step chain: identical positions AND
     bit-identical responses (same arithmetic, only the SM a window runs on changes); hand-off scratch left clean
-    (a second chained call gives the same answer)."""
+    (a second chained call gives the same answer); the plain launch's co-residency handshake and its static fall-back."""
     import torch
     n, T, H, W = 240, 11, 96, 128
     rng = np.random.default_rng(77)
@@ -642,10 +642,24 @@ def test_rotating_slots_equal_static_split(gpu_pkg, dtype):
         b.set_guess(start)
         ij_st, r_st = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
         assert b.last_kernel == "dog_window45_argmax"
+        # the kernel's own fall-back: its co-residency handshake settles on the static schedule (what happens when the
+        # device is shared and the CTAs cannot all be resident) — and the next launch rotates again
+        b.set_option("rot", 3)
+        b.set_guess(start)
+        ij_fb, r_fb = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_rot"
+        b.set_option("rot", 1)
+        b.set_guess(start)
+        ij_rot3, r_rot3 = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_rot"
     np.testing.assert_array_equal(ij_rot, ij_st)
     np.testing.assert_array_equal(r_rot, r_st)
     np.testing.assert_array_equal(ij_rot2, ij_st)
     np.testing.assert_array_equal(r_rot2, r_st)
+    np.testing.assert_array_equal(ij_fb, ij_st)
+    np.testing.assert_array_equal(r_fb, r_st)
+    np.testing.assert_array_equal(ij_rot3, ij_st)
+    np.testing.assert_array_equal(r_rot3, r_st)
 
 
 def test_float32_frames_chained_and_batched(gpu_pkg, oracle, synth):

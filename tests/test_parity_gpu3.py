@@ -1,0 +1,150 @@
+"""GPU parity tests, round 2 (second part): target widths below 25 and windows below 45x45 through the per-window
+kernels (dog_window45_argmax / _rot / _cluster<C>).  Those kernels are compiled for l = 65 and 45x45 outputs; a shorter
+kernel runs zero-padded (0·x changes no sum), a smaller window masks the surplus outputs and skips footprint rows and
+column groups without work.  Every variant against the oracle loop: positions exact, responses within RTOL·max|R|;
+and against the generic streaming kernel (the path these geometries took before).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+# a window that sees nothing but the border fill: the GPU path gives exactly 0, the f64 oracle its rounding noise (1e-16)
+BLANK = 1e-12
+
+
+def default_window(tw):
+    import math
+    return 4 * math.ceil(tw / (2 * math.sqrt(2 * math.log(2)))) + 1          # src/PawsomeTracker.jl:64-68
+
+
+def oracle_chain(oracle, frames, tw, darker, ws, start_guess, fill):
+    g = tuple(int(x) for x in start_guess)
+    pos, resp, mx, near = [], [], [], 0
+    for f in frames:
+        r = oracle.step(f, fill, tw, darker, ws, g, dense=True)
+        near += r.near_tie(RTOL)
+        g = (r.i, r.j)
+        pos.append(g); resp.append(r.resp); mx.append(r.maxabs)
+    return np.array(pos), np.array(resp), np.array(mx), near
+
+
+def make_case(synth, H, W, n, T, tw, darker, seed):
+    vids = [synth.make_video(H=H, W=W, target_width=tw, start_ij=(H // 2, W // 2), seconds=10.0, fps=24.0, seed=seed + s,
+                             darker_target=darker) for s in range(n)]
+    frames = np.stack([np.stack([v.frame(t) for v in vids]) for t in range(T)])
+    start = np.tile([H // 2, W // 2], (n, 1)).astype(np.int32)
+    if n > 2:
+        start[1] = (2, 3)                 # the window hangs over the top-left corner
+        start[2] = (H + 7, W - 1)         # a guess outside the frame
+    return frames, start
+
+
+@pytest.mark.parametrize("tw,ws,darker", [
+    (10, None, True), (15, None, True), (20, None, False), (22.5, None, True), (12, (21, 33), True),
+    (25, (31, 45), True), (25, (45, 17), False), (8, (5, 9), True), (25, (1, 1), True),
+])
+def test_small_geometries_through_the_window_kernels(gpu_pkg, oracle, synth, tw, ws, darker):
+    """Chained steps of 7 videos (one SM each) and of the same videos through the cluster kernel (2, 4, 8 CTAs per
+    window, TMA and global-load staging), against the oracle loop and the generic kernel."""
+    import torch
+    ws = ws or (default_window(tw),) * 2
+    n, T, H, W = 7, 6, 160, 208
+    frames, start = make_case(synth, H, W, n, T, tw, darker, 500)
+    dev = torch.from_numpy(frames).cuda()
+    results = {}
+    with gpu_pkg.TrackerBatch(n, (H, W), tw, ws, darker) as b:
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        fills = b.compute_fill()
+        for name, opts in [("per-SM", {"cluster": 1}), ("C2", {"cluster": 2, "bulk": 1}), ("C4", {"cluster": 4, "bulk": 0}),
+                           ("C8", {"cluster": 8, "bulk": 1}), ("generic", {"window45": 0})]:
+            for k, v in opts.items():
+                b.set_option(k, v)
+            b.set_guess(start)
+            results[name] = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+            if name == "per-SM":
+                assert b.last_kernel == "dog_window45_argmax"
+            elif name.startswith("C"):
+                assert b.last_kernel == f"dog_window45_cluster<{name[1]}>"
+            else:
+                assert b.last_kernel.startswith("dog_rect_argmax")
+    ij0, r0 = results["per-SM"]
+    for name in ("C2", "C4", "C8"):
+        np.testing.assert_array_equal(results[name][0], ij0)
+        np.testing.assert_array_equal(results[name][1], r0)           # same per-output operation order: bit-identical
+    for v in range(n):
+        pos, resp, mx, near = oracle_chain(oracle, [frames[t, v] for t in range(T)], tw, darker, ws, start[v], int(fills[v]))
+        if near == 0:
+            np.testing.assert_array_equal(ij0[:, v], pos)
+            np.testing.assert_array_equal(results["generic"][0][:, v], pos)
+        assert np.all(np.abs(r0[:, v] - resp) <= np.maximum(RTOL * mx, BLANK))
+
+
+@pytest.mark.parametrize("tw,dtype", [(10, np.uint8), (20, np.uint8), (15, np.float32)])
+def test_small_geometries_in_large_batches(gpu_pkg, oracle, tw, dtype):
+    """More windows than SMs: the static split (two windows per SM) and the rotating-slot kernel, 11 chained steps of
+    random-noise frames (every response value informative) — identical to each other, a sample against the oracle."""
+    import torch
+    ws = (default_window(tw),) * 2
+    n, T, H, W = 230, 11, 96, 128
+    rng = np.random.default_rng(int(tw))
+    base = rng.integers(0, 256, (T, n, H, W)).astype(np.uint8)
+    frames = base if dtype is np.uint8 else base.astype(np.float32) / np.float32(255.0)
+    dev = torch.from_numpy(frames).cuda()
+    start = np.stack([rng.integers(1, H + 1, n), rng.integers(1, W + 1, n)], axis=-1)
+    with gpu_pkg.TrackerBatch(n, (H, W), tw, ws, True, dtype=dtype) as b:
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        fills = b.compute_fill()
+        b.set_option("rot", 2)
+        b.set_guess(start)
+        ij_rot, r_rot = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_rot"
+        b.set_option("rot", 0)
+        b.set_guess(start)
+        ij_st, r_st = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel == "dog_window45_argmax"
+    np.testing.assert_array_equal(ij_rot, ij_st)
+    np.testing.assert_array_equal(r_rot, r_st)
+    for v in (0, 1, 77, 148, n - 1):
+        pos, resp, mx, near = oracle_chain(oracle, [base[t, v] for t in range(T)], tw, True, ws, start[v], int(fills[v]))
+        if near == 0:
+            np.testing.assert_array_equal(ij_st[:, v], pos)
+        assert np.all(np.abs(r_st[:, v] - resp) <= np.maximum(RTOL * mx, BLANK))
+
+
+def test_small_geometry_host_paths_and_single_tracker(gpu_pkg, oracle, synth):
+    """Tracker(img, 15, default window) — the per-frame call on a host frame, the resident step, the response map
+    (marching kernel with zero-padded taps) and track() on pageable and page-locked frames."""
+    tw = 15
+    ws = (default_window(tw),) * 2
+    vid = synth.make_video(H=240, W=320, target_width=tw, start_ij=(120, 160), seconds=4.0, fps=24.0, seed=3)
+    frames = np.stack([vid.frame(k) for k in range(40)])
+    fill = oracle.mode(frames[0])
+    trk = gpu_pkg.Tracker(frames[0], tw, ws, True)
+    try:
+        g = (118, 163)
+        ref = oracle.step(frames[0], fill, tw, True, ws, g, dense=True, want_map=True)
+        assert trk(g) == (ref.i, ref.j)
+        assert abs(trk.last_response - ref.resp) <= RTOL * ref.maxabs
+        assert trk.step_resident(g) == (ref.i, ref.j)
+        rmap = trk.response_map(g)
+        assert np.abs(rmap - ref.R).max() <= RTOL * ref.maxabs
+    finally:
+        trk.close()
+    pos, _, _, near = oracle_chain(oracle, list(frames), tw, True, ws, (120, 160), fill)
+    assert near == 0
+    for pinned in (False, True):
+        pin = None
+        src = frames
+        if pinned:
+            pin = gpu_pkg.PinnedArray(frames.shape, np.uint8)
+            pin.array[...] = frames
+            src = pin.array
+        av = gpu_pkg.ArrayVideo(src, fps=24.0)
+        ts, ij = gpu_pkg.track(av, stop=len(frames) / 24.0, target_width=tw, start_location=gpu_pkg.CartesianIndex(120, 160),
+                               darker_target=True, fps=24)
+        np.testing.assert_array_equal(np.asarray(ij), pos)
+        if pin is not None:
+            del av
+            pin.close()

@@ -22,8 +22,26 @@ def load():
         L.ptb_probe_ffma2_issue.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.ptb_flush_l2.restype = C.c_int
         L.ptb_flush_l2.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ptb_time_chain.restype = C.c_int
+        L.ptb_time_chain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int),
+                                     C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
     return _lib
+
+
+def time_chain(product_lib, batch, segments, step_stride: int, frame_stride: int, pitch: int, stream: int) -> float:
+    """Device time (ms) of pt_batch_track_device_async over `segments` = [(device pointer, steps), ...] on `stream`:
+    event, launches, event issued back to back from C (ptb_time_chain); returns after the second event completed."""
+    fn = C.cast(product_lib.pt_batch_track_device_async, C.c_void_p)
+    nseg = len(segments)
+    bases = (C.c_void_p * nseg)(*[int(p) for p, _ in segments])
+    Ts = (C.c_int * nseg)(*[int(t) for _, t in segments])
+    ms = C.c_double()
+    rc = load().ptb_time_chain(fn, batch._h, nseg, bases, Ts, step_stride, frame_stride, pitch,
+                               C.c_void_p(stream) if stream else None, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"ptb_time_chain failed ({rc})")
+    return ms.value
 
 
 def fp32_peak(device: int, packed: int, reps: int = 5) -> float:

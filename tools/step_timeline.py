@@ -44,3 +44,6 @@ for t in range(T):
     prev = med
 print(f"last step starts: median {np.median(st[:, -1]):.1f}, max {st[:, -1].max():.1f}; kernel end (event) - first start unknown; "
       f"event time - last median start = {ms*1e3 - np.median(st[:, -1]):.1f} us (includes launch latency before the first start)")
+if os.environ.get("PT_TIMELINE_DUMP"):
+    os.makedirs(os.path.dirname(os.environ["PT_TIMELINE_DUMP"]) or ".", exist_ok=True)
+    np.save(os.environ["PT_TIMELINE_DUMP"], d)
