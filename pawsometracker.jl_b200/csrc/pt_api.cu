@@ -211,6 +211,7 @@ const pt::Cfg &defaults_from_env()
         cfg.cluster = geti("PT_W45_CLUSTER", 0);
         cfg.bulk = geti("PT_W45_BULK", 1) ? 1 : 0;
         cfg.wide = geti("PT_GENERIC_WIDE", 1) ? 1 : 0;
+        cfg.two_phase = geti("PT_WIDE_TWO_PHASE", 1);
     });
     return cfg;
 }
@@ -255,6 +256,7 @@ struct pt_lane {
     PinnedBuf h_crops, h_res;
     DevBuf d_crops;
     int v0 = 0, v1 = 0, index = 0;
+    float2 *d_mid = nullptr;             // slice of pt_batch::d_mid for this lane's windows (two-phase wide path)
 };
 
 struct pt_batch {
@@ -307,6 +309,7 @@ struct pt_batch {
     pt::Cfg cfg;                         // tuning / debugging knobs (defaults_from_env at create, pt_batch_set_option)
     cudaStream_t ext_stream = nullptr;   // caller stream of the most recent pt_batch_track_device_async (may still run)
     PinnedBuf h_small;                   // pinned staging for the small synchronous uploads (fills, centres, taps)
+    DevBuf d_mid;                        // row-pass intermediate of the two-phase wide path ([n] windows), grown on demand
 };
 
 struct pt_tracker {
@@ -353,6 +356,7 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     a.frame_ptrs = nullptr;
     a.xflag = (nwin == b->n) ? b->d_xflag : nullptr;     // whole-batch launches only (one stream at a time)
     a.xpos = b->d_xpos;
+    a.mid = nullptr;
     (void)nwin;
     return a;
 }
@@ -384,6 +388,39 @@ void decompose(pt::WinArgs &a, int nwin, int target)
     a.chunks = (a.wr + a.CH - 1) / a.CH;
 }
 
+// Row chunks of the column-pass launch of the two-phase wide path.  Chunks cost no arithmetic here, only a re-read of
+// 2w intermediate rows from L2 each; a CTA's cost ≈ copies (≈ 150 cycles per 32 rows, asynchronous) + column pass (32·Lq16 cycles per
+// 32 output rows), CTAs are uniform, so the launch costs whole waves of them.
+void decompose_cols(pt::WinArgs &a, int nwin, int sms)
+{
+    a.strips = (a.wc + 2 * pt::kTileCols - 1) / (2 * pt::kTileCols);
+    const int nbo = (a.wr + pt::kBatchRows - 1) / pt::kBatchRows;
+    const double colc = 32.0 * (double)(((a.L + 1 + 15) / 16) * 16), cpy = 150.0;
+    double best = 1e300;
+    int best_k = 1;
+    for (int k = 1; k <= nbo; ++k) {
+        const int CH = k * pt::kBatchRows, chunks = (a.wr + CH - 1) / CH;
+        const long long ctas = (long long)nwin * a.strips * chunks;
+        const double waves = (double)((ctas + sms - 1) / sms);
+        const double cost = waves * (cpy * (double)((CH + 2 * a.w + pt::kBatchRows - 1) / pt::kBatchRows) + colc * k);
+        if (cost < best - 1e-9) { best = cost; best_k = k; }
+    }
+    a.CH = best_k * pt::kBatchRows;
+    a.chunks = (a.wr + a.CH - 1) / a.CH;
+}
+
+// Two launches (row pass of every footprint batch once, then the column pass) instead of the fused wide kernel?
+// Fused, a launch that cannot fill the GPU with whole strips cuts them into row chunks and repeats 2w footprint rows
+// of the row pass per chunk; two-phase, CTAs are small and uniform (no wave quantisation of one-CTA-per-SM strips).
+bool want_two_phase(const pt_batch *b, const pt::WinArgs &a, int nwin)
+{
+    if (!a.mid || b->cfg.two_phase == 0 || pt::wide_cols_smem_bytes(a.L) + 512 > (size_t)b->cfg.smem_optin) return false;
+    // measured (tools/config4_timing.py, tools/tw_sweep.py): faster than the fused kernel for every batch size — one
+    // 401x401 window at l = 245: 25 vs 74 µs, 64 of them: 690 vs 725 µs, 256 windows at tw = 70: 225 vs 293 µs
+    (void)nwin;
+    return true;
+}
+
 // Kernel choice shared by every path (so host-footprint, resident and per-step calls round identically).
 // Thread-safe: touches no batch state.
 cudaError_t launch_windows(const pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
@@ -393,20 +430,43 @@ cudaError_t launch_windows(const pt_batch *b, pt::WinArgs &a, int nwin, cudaStre
     if (b->cfg.window45 && pt::rect45_supported(a, b->cfg, b->pixel))
         return pt::launch_rect45(a, b->cfg, nwin, b->pixel, s);
     a.wide = use_wide_kernel(b, a) ? 1 : 0;
-    decompose(a, nwin, b->cfg.generic_target);
+    if (!(a.wide && want_two_phase(b, a, nwin))) a.mid = nullptr;
+    if (a.mid) decompose_cols(a, nwin, b->cfg.sms);
+    else decompose(a, nwin, b->cfg.generic_target);
     return a.wide ? pt::launch_wide(a, nwin, b->pixel, s) : pt::launch_generic(a, nwin, b->pixel, s);
+}
+
+// Grow the two-phase intermediate for nwin windows of a's geometry (no-op for the other kernels); leaves a.mid null
+// when the buffer would be unreasonably large.
+int ensure_mid(pt_batch *b, pt::WinArgs &a, int nwin, size_t window_offset = 0)
+{
+    a.mid = nullptr;
+    if (b->cfg.two_phase == 0 || (b->cfg.window45 && (pt::window45_supported(a, b->pixel) || pt::rect45_supported(a, b->cfg, b->pixel))) ||
+        !use_wide_kernel(b, a))
+        return PT_OK;
+    const size_t per = pt::wide_mid_elems(a.L, a.wr, a.wc, 1);
+    const size_t bytes = per * sizeof(float2) * (window_offset + (size_t)nwin);
+    if (bytes > ((size_t)2 << 30)) return PT_OK;
+    int rc = b->d_mid.ensure(bytes, b);
+    if (rc) return rc;
+    a.mid = (float2 *)b->d_mid.p + per * window_offset;
+    return PT_OK;
 }
 
 int launch_step(pt_batch *b, pt::WinArgs &a, int nwin, cudaStream_t s)
 {
+    int rcm = ensure_mid(b, a, nwin);
+    if (rcm) return rcm;
+    const bool two = a.mid != nullptr && use_wide_kernel(b, a) && want_two_phase(b, a, nwin);
     const cudaError_t e = launch_windows(b, a, nwin, s);
     if (b->cfg.window45 && !a.rect_mode && !a.map_out && pt::window45_supported(a, b->pixel))
         b->last_kernel = pt::window45_kernel_for(a, b->cfg, nwin, b->pixel);
     else if (b->cfg.window45 && pt::rect45_supported(a, b->cfg, b->pixel)) b->last_kernel = pt::rect45_name();
-    else if (use_wide_kernel(b, a)) b->last_kernel = b->pixel == PT_PIX_U8 ? "dog_rect_argmax_wide<u8>" : "dog_rect_argmax_wide<f32>";
+    else if (use_wide_kernel(b, a)) b->last_kernel = two ? (b->pixel == PT_PIX_U8 ? "dog_rows_wide<u8>+dog_cols_wide" : "dog_rows_wide<f32>+dog_cols_wide")
+                                                        : (b->pixel == PT_PIX_U8 ? "dog_rect_argmax_wide<u8>" : "dog_rect_argmax_wide<f32>");
     else b->last_kernel = b->pixel == PT_PIX_U8 ? "dog_rect_argmax_generic<u8>" : "dog_rect_argmax_generic<f32>";
     if (e != cudaSuccess) return fail(PT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-    b->launches += 1;
+    b->launches += two ? 2 : 1;
     return PT_OK;
 }
 
@@ -681,7 +741,7 @@ void pt_batch_destroy(pt_batch *b)
         if (b->ev_copy[i]) cudaEventDestroy(b->ev_copy[i]);
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
     }
-    b->d_traj_pos.release(); b->d_traj_resp.release(); b->d_map.release(); b->h_out.release();
+    b->d_traj_pos.release(); b->d_traj_resp.release(); b->d_map.release(); b->h_out.release(); b->d_mid.release();
     b->d_ptrs.release(); b->h_traj.release(); b->h_ptrs.release();
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
@@ -945,6 +1005,7 @@ void lane_worker(HostTrack *ht, pt_lane *ln)
             a.fill = b->d_fill + ln->v0;
             a.keys = b->d_keys + ln->v0; a.counters = b->d_counters + ln->v0; a.tickets = b->d_counters + b->n + 2 * ln->v0;
             a.out_pos = hres; a.out_resp = hresp;      // pinned + mapped: the kernel stores the results straight into host memory
+            a.mid = ln->d_mid;                         // (two-phase wide path: this lane's slice of the intermediate, or null)
             e = launch_windows(b, a, nl, ln->stream);
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(ln->stream);
@@ -990,6 +1051,14 @@ int ensure_lanes(pt_batch *b)
         int rc = ln.h_crops.ensure(cp * fr * es * nl, b); if (rc) return rc;
         rc = ln.d_crops.ensure(cp * fr * es * nl, b); if (rc) return rc;
         rc = ln.h_res.ensure(nl * 20, b); if (rc) return rc;
+    }
+    {
+        // two-phase wide path: one intermediate for the whole batch, a slice per lane (crops are fr x fc "frames")
+        pt::WinArgs probe = make_args(b, nullptr, 0, cp, fr, fc, b->d_center, b->n);
+        int rc = ensure_mid(b, probe, b->n);
+        if (rc) return rc;
+        const size_t per = pt::wide_mid_elems(b->L, b->wr, b->wc, 1);
+        for (auto &ln : b->lanes) ln.d_mid = probe.mid ? probe.mid + per * (size_t)ln.v0 : nullptr;
     }
     if (b->center_key[0] != b->rr || b->center_key[1] != b->rc || b->center_key[2] != b->w) {
         std::vector<int2> c(b->n, make_int2(b->rr + b->w + 1, b->rc + b->w + 1));
@@ -1219,7 +1288,7 @@ int pt_batch_set_option(pt_batch *b, const char *name, int value)
         {"mode_slow", &pt::Cfg::mode_slow, 0, 1},     {"zero_copy", &pt::Cfg::zero_copy, 0, 1},
         {"host_lanes", &pt::Cfg::host_lanes, 0, 1024}, {"cluster", &pt::Cfg::cluster, 0, 8},
         {"bulk", &pt::Cfg::bulk, 0, 1},
-        {"wide", &pt::Cfg::wide, 0, 1},
+        {"wide", &pt::Cfg::wide, 0, 1},               {"two_phase", &pt::Cfg::two_phase, 0, 2},
     };
     for (const Opt &o : opts) {
         if (strcmp(o.name, name) != 0) continue;

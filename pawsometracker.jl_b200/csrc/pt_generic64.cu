@@ -136,7 +136,135 @@ __device__ __forceinline__ void stage64_words(const uint8_t *frame, int pitch, i
     }
 }
 
+
+// ---- row pass of one thread: 8 consecutive outputs of one staged row (ctr = x(c), c = centre of output 0)
+__device__ __forceinline__ void row_pass64(const float *ctr, const WideTaps &wt, int w16, float2 (&acc)[R64])
+{
+    float Lb[U64], Rb[U64];
+    {
+        const float2 g0 = wt.trow[0];
+#pragma unroll
+        for (int j = 0; j < R64; ++j) { const float x0 = ctr[j]; acc[j] = make_float2(x0 * g0.x, x0 * g0.y); }
+    }
+#pragma unroll
+    for (int k = -6; k <= 4; ++k) Lb[k & 15] = ctr[-k];         // xl(-6 … 4)
+#pragma unroll
+    for (int k = 1; k <= 11; ++k) Rb[k & 15] = ctr[k];          // xr(1 … 11)
+    const float *pl = ctr, *pr = ctr;
+#pragma unroll 1
+    for (int d0 = 0; d0 < w16; d0 += U64) {
+#pragma unroll
+        for (int u = 0; u < U64; ++u) {
+            const int d = u + 1;                                  // step d0 + d; slots depend on d mod 16 only
+            Lb[(d + 4) & 15] = pl[-(d + 4)];                      // xl(d0 + d + 4)
+            Rb[(d + 11) & 15] = pr[d + 11];                       // xr(d0 + d + 11)
+            const float2 g = wt.trow[d0 + d];                     // warp-uniform index → uniform registers
+#pragma unroll
+            for (int j = 0; j < R64; ++j) {
+                const float sm = Lb[(d - j) & 15] + Rb[(d + j) & 15];
+                acc[j] = ffma2w(make_float2(sm, sm), g, acc[j]);
+            }
+        }
+        pl -= U64; pr += U64;
+    }
+}
+
+// ---- column pass + running argmax for the 32 output rows whose support is complete with batch b of a chunk:
+// lane = output column (warps w and w + 4 side by side cover 64), warp & 3 = group of 8 output rows.
+// Outputs (2p, 2p+1) share a packed accumulator: the ring row met at tap q by output 2p meets tap q−1 at output
+// 2p+1.  Ring rows are numbered n = footprint row − f_first with f_first = o0 − δ a multiple of 8, kept in a
+// 16-slot circular register buffer (slot = n mod 16) and fetched 12 rows ahead in contiguous runs of 8.
+template <int DELTA>
+__device__ __forceinline__ void col_pass64(const WinArgs &a, const WideTaps &wt, const Geom64 &G, const float2 *s_ring, int b,
+                                           int w, int ch, int sw, int c0, int r0, int v, int warp, int lane,
+                                           float &best_v, unsigned int &best_i, int pad = 0)
+{
+    // ring row f holds footprint row f − pad of the chunk (pad = 0 in the fused kernel; the two-phase column kernel
+    // shifts the rows so that whole 32-row output batches complete together)
+    const int o_base = b * TB64 - 2 * w - pad;   // first output row whose support is complete with this batch
+    if (o_base + TB64 > 0 && o_base < ch && 32 * (warp >> 2) < sw) {
+        // warps 0-3 take the left 32 columns (one row group each → one warp per scheduler), warps 4-7 the right
+        // 32: a strip of ≤ 32 columns keeps all four schedulers busy with half the work
+        const int col = lane + 32 * (warp >> 2);
+        const int o0 = o_base + R64 * (warp & 3);
+        const int f_first = o0 + pad - DELTA;                         // ≡ 0 (mod 8)
+        int s0 = f_first % G.nring;
+        if (s0 < 0) s0 += G.nring;
+        const float2 *ring_lo = s_ring + col, *ring_hi = s_ring + (size_t)G.nring * RP64 + col;
+        const float2 *run = ring_lo + (size_t)s0 * RP64;              // run of 8 rows holding n = 0 … 7
+        float2 D[U64];
+        float2 accP[R64 / 2], accM[R64 / 2];
+#pragma unroll
+        for (int p = 0; p < R64 / 2; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int n = 0; n < 8; ++n) D[n] = run[n * RP64];
+        run += 8 * RP64; if (run >= ring_hi) run -= (size_t)G.nring * RP64;
+#pragma unroll
+        for (int n = 8; n < 12; ++n) D[n] = run[(n - 8) * RP64];      // run now holds n = 8 … 15
+#pragma unroll 1
+        for (int q0 = 0; q0 < G.Lq16; q0 += U64) {
+#pragma unroll
+            for (int u = 0; u < U64; ++u) {
+                // fetch row n = q0 + u + 12 (run-relative index (u + 4) mod 8; a new run starts at u = 4 and u = 12)
+                if (u == 4 || u == 12) { run += 8 * RP64; if (run >= ring_hi) run -= (size_t)G.nring * RP64; }
+                D[(u + 12) & 15] = run[((u + 4) & 7) * RP64];
+                const float4 gq = wt.cq[q0 + u];                      // warp-uniform index → uniform registers
+                const float2 gp = make_float2(gq.x, gq.y), gm = make_float2(gq.z, gq.w);
+#pragma unroll
+                for (int p = 0; p < R64 / 2; ++p) {
+                    const float2 m = D[(DELTA + 2 * p + u) & 15];
+                    accP[p] = ffma2w(make_float2(m.x, m.x), gp, accP[p]);
+                }
+#pragma unroll
+                for (int p = 0; p < R64 / 2; ++p) {
+                    const float2 m = D[(DELTA + 2 * p + u) & 15];
+                    accM[p] = ffma2w(make_float2(m.y, m.y), gm, accM[p]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R64; ++j) {
+            const int o = o0 + j;
+            if (o >= 0 && o < ch && col < sw) {
+                const float val = ((j & 1) ? accP[j / 2].y + accM[j / 2].y : accP[j / 2].x + accM[j / 2].x) + 0.0f;
+                const unsigned int idx = (unsigned int)(c0 + col) * (unsigned int)a.wr + (unsigned int)(r0 + o);
+                if (val > best_v || (val == best_v && idx < best_i)) { best_v = val; best_i = idx; }
+                if (a.map_out)
+                    a.map_out[(size_t)v * a.wr * a.wc + (size_t)(r0 + o) * a.wc + (c0 + col)] = val;
+            }
+        }
+    }
+}
+
 } // namespace
+
+// ---- block argmax → one 64-bit atomicMax per CTA; the last CTA of a window decodes, clamps and publishes
+__device__ __forceinline__ void merge_and_publish64(const WinArgs &a, int v, int wy0, int wx0, float best_v, unsigned int best_i,
+                                                    unsigned long long *s_best, int tid, int warp, int lane)
+{
+    unsigned long long key = (best_i == 0xFFFFFFFFu) ? 0ull : pack_key(best_v, best_i);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+        key = o > key ? o : key;
+    }
+    if (lane == 0) s_best[warp] = key;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long k = s_best[0];
+        for (int i = 1; i < WARPS64; ++i) k = s_best[i] > k ? s_best[i] : k;
+        atomicMax(a.keys + v, k);
+        __threadfence();
+        const unsigned int total = (unsigned int)(a.strips * a.chunks);
+        const unsigned int prev = atomicAdd(a.counters + v, 1u);
+        if (prev == total - 1u) {
+            __threadfence();
+            const unsigned long long win = atomicExch(a.keys + v, 0ull);
+            a.counters[v] = 0u;
+            publish_result(a, v, win, wy0, wx0);
+        }
+    }
+}
 
 template <typename PixT, int DELTA>
 __global__ void __launch_bounds__(THREADS64, 1)
@@ -214,35 +342,8 @@ dog_rect_argmax_wide(const __grid_constant__ WinArgs a, const __grid_constant__ 
         // Left values xl(k) = x(c − k), k ∈ [d−7, d] at step d, right values xr(k) = x(c + k), k ∈ [d, d+7]: both live in
         // 16-slot circular register buffers (slot = k mod 16) and are fetched 4 steps ahead.
         if (warp * R64 < sw) {
-            const float *ctr = s_in + lane * G.pin + LPAD + G.w16 + warp * R64;     // x(c), c = centre of output 0
             float2 acc[R64];
-            float Lb[U64], Rb[U64];
-            {
-                const float2 g0 = wt.trow[0];
-#pragma unroll
-                for (int j = 0; j < R64; ++j) { const float x0 = ctr[j]; acc[j] = make_float2(x0 * g0.x, x0 * g0.y); }
-            }
-#pragma unroll
-            for (int k = -6; k <= 4; ++k) Lb[k & 15] = ctr[-k];         // xl(-6 … 4)
-#pragma unroll
-            for (int k = 1; k <= 11; ++k) Rb[k & 15] = ctr[k];          // xr(1 … 11)
-            const float *pl = ctr, *pr = ctr;
-#pragma unroll 1
-            for (int d0 = 0; d0 < G.w16; d0 += U64) {
-#pragma unroll
-                for (int u = 0; u < U64; ++u) {
-                    const int d = u + 1;                                  // step d0 + d; slots depend on d mod 16 only
-                    Lb[(d + 4) & 15] = pl[-(d + 4)];                      // xl(d0 + d + 4)
-                    Rb[(d + 11) & 15] = pr[d + 11];                       // xr(d0 + d + 11)
-                    const float2 g = wt.trow[d0 + d];                     // warp-uniform index → uniform registers
-#pragma unroll
-                    for (int j = 0; j < R64; ++j) {
-                        const float sm = Lb[(d - j) & 15] + Rb[(d + j) & 15];
-                        acc[j] = ffma2w(make_float2(sm, sm), g, acc[j]);
-                    }
-                }
-                pl -= U64; pr += U64;
-            }
+            row_pass64(s_in + lane * G.pin + LPAD + G.w16 + warp * R64, wt, G.w16, acc);
             const int f = b * TB64 + lane;
             float2 *dst = s_ring + (size_t)(f % G.nring) * RP64 + warp * R64;
 #pragma unroll
@@ -250,94 +351,150 @@ dog_rect_argmax_wide(const __grid_constant__ WinArgs a, const __grid_constant__ 
         }
         __syncthreads();
 
-        // ---- column pass: lane = output column (warps w and w + 4 side by side cover 64), warp & 3 = group of 8 output rows.
-        // Outputs (2p, 2p+1) share a packed accumulator: the ring row met at tap q by output 2p meets tap q−1 at output
-        // 2p+1.  Ring rows are numbered n = footprint row − f_first with f_first = o0 − δ a multiple of 8, kept in a
-        // 16-slot circular register buffer (slot = n mod 16) and fetched 12 rows ahead in contiguous runs of 8.
-        const int o_base = b * TB64 - 2 * w;   // first output row whose support is complete with this batch
-        if (o_base + TB64 > 0 && o_base < ch && 32 * (warp >> 2) < sw) {
-            // warps 0-3 take the left 32 columns (one row group each → one warp per scheduler), warps 4-7 the right
-            // 32: a strip of ≤ 32 columns keeps all four schedulers busy with half the work
-            const int col = lane + 32 * (warp >> 2);
-            const int o0 = o_base + R64 * (warp & 3);
-            const int f_first = o0 - DELTA;                               // ≡ 0 (mod 8)
-            int s0 = f_first % G.nring;
-            if (s0 < 0) s0 += G.nring;
-            const float2 *ring_lo = s_ring + col, *ring_hi = s_ring + (size_t)G.nring * RP64 + col;
-            const float2 *run = ring_lo + (size_t)s0 * RP64;              // run of 8 rows holding n = 0 … 7
-            float2 D[U64];
-            float2 accP[R64 / 2], accM[R64 / 2];
-#pragma unroll
-            for (int p = 0; p < R64 / 2; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
-#pragma unroll
-            for (int n = 0; n < 8; ++n) D[n] = run[n * RP64];
-            run += 8 * RP64; if (run >= ring_hi) run -= (size_t)G.nring * RP64;
-#pragma unroll
-            for (int n = 8; n < 12; ++n) D[n] = run[(n - 8) * RP64];      // run now holds n = 8 … 15
-#pragma unroll 1
-            for (int q0 = 0; q0 < G.Lq16; q0 += U64) {
-#pragma unroll
-                for (int u = 0; u < U64; ++u) {
-                    // fetch row n = q0 + u + 12 (run-relative index (u + 4) mod 8; a new run starts at u = 4 and u = 12)
-                    if (u == 4 || u == 12) { run += 8 * RP64; if (run >= ring_hi) run -= (size_t)G.nring * RP64; }
-                    D[(u + 12) & 15] = run[((u + 4) & 7) * RP64];
-                    const float4 gq = wt.cq[q0 + u];                      // warp-uniform index → uniform registers
-                    const float2 gp = make_float2(gq.x, gq.y), gm = make_float2(gq.z, gq.w);
-#pragma unroll
-                    for (int p = 0; p < R64 / 2; ++p) {
-                        const float2 m = D[(DELTA + 2 * p + u) & 15];
-                        accP[p] = ffma2w(make_float2(m.x, m.x), gp, accP[p]);
-                    }
-#pragma unroll
-                    for (int p = 0; p < R64 / 2; ++p) {
-                        const float2 m = D[(DELTA + 2 * p + u) & 15];
-                        accM[p] = ffma2w(make_float2(m.y, m.y), gm, accM[p]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < R64; ++j) {
-                const int o = o0 + j;
-                if (o >= 0 && o < ch && col < sw) {
-                    const float val = ((j & 1) ? accP[j / 2].y + accM[j / 2].y : accP[j / 2].x + accM[j / 2].x) + 0.0f;
-                    const unsigned int idx = (unsigned int)(c0 + col) * (unsigned int)a.wr + (unsigned int)(r0 + o);
-                    if (val > best_v || (val == best_v && idx < best_i)) { best_v = val; best_i = idx; }
-                    if (a.map_out)
-                        a.map_out[(size_t)v * a.wr * a.wc + (size_t)(r0 + o) * a.wc + (c0 + col)] = val;
-                }
-            }
-        }
+        // ---- column pass for the output rows whose support is complete with this batch
+        col_pass64<DELTA>(a, wt, G, s_ring, b, w, ch, sw, c0, r0, v, warp, lane, best_v, best_i);
         // the next batch's staging only touches s_in; its row pass (which overwrites the oldest ring rows read above)
         // runs after the next barrier
     }
 
-    // ---- block argmax → one 64-bit atomicMax per CTA
-    unsigned long long key = (best_i == 0xFFFFFFFFu) ? 0ull : pack_key(best_v, best_i);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, off);
-        key = o > key ? o : key;
-    }
-    if (lane == 0) s_best[warp] = key;
+    merge_and_publish64(a, v, wy0, wx0, best_v, best_i, s_best, tid, warp, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Two-phase variant for launches that cannot fill the GPU with whole strips (a single 4K video with a 401×401 window at
+// l = 245 is 7 strips): splitting a strip into row chunks repeats 2w footprint rows of the row pass per chunk (at 21
+// chunks 6× the arithmetic).  Instead
+//   dog_rows_wide   row-filters every (32-row batch, 64-column strip) of the window's footprint exactly once — all
+//                   batches are independent, 147 CTAs for the 4K window — and writes the (narrow, wide) intermediate
+//                   to global memory (L2-resident: 2.3 MB per window);
+//   dog_cols_wide   runs the column pass + argmax per (row chunk, strip): it copies the chunk's intermediate rows into
+//                   the ring (the redundancy between chunks is now a re-READ of 2w rows from L2, not arithmetic) and
+//                   then is the fused kernel's column pass and merge.
+// Same per-output operation order as the fused kernel: bit-identical responses.
+// ---------------------------------------------------------------------------------------------------
+template <typename PixT>
+__global__ void __launch_bounds__(THREADS64, 2)
+dog_rows_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTaps wt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = a.L, w = a.w;
+    const Geom64 G = geom64(L);
+    float *s_in = reinterpret_cast<float *>(smem_raw);                    // [32][pin]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nfoot = a.wr + 2 * w, nbt = (nfoot + TB64 - 1) / TB64;
+    const int id = (int)blockIdx.x;
+    const int strip = id % a.strips, r = id / a.strips, b = r % nbt, v = r / nbt;
+    int wy0, wx0;
+    if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
+    else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
+    const int c0 = strip * SW64, sw = min(SW64, a.wc - c0);
+    for (int e = tid; e < TB64 * G.pin; e += THREADS64) s_in[e] = 0.f;      // incl. the never-used pad columns
+    const float fill = a.fill[v];
+    const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
+    const int X0 = wx0 + c0 - G.w16, Yb = wy0 - w;
+    const bool words_ok = sizeof(PixT) == 1 && ((reinterpret_cast<uintptr_t>(frame) | (uintptr_t)a.pitch) & 3u) == 0 &&
+                          a.pitch >= ((a.W + 3) & ~3);
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long k = s_best[0];
-        for (int i = 1; i < WARPS64; ++i) k = s_best[i] > k ? s_best[i] : k;
-        atomicMax(a.keys + v, k);
-        __threadfence();
-        const unsigned int total = (unsigned int)(a.strips * a.chunks);
-        const unsigned int prev = atomicAdd(a.counters + v, 1u);
-        if (prev == total - 1u) {
-            __threadfence();
-            const unsigned long long win = atomicExch(a.keys + v, 0ull);
-            a.counters[v] = 0u;
-            publish_result(a, v, win, wy0, wx0);
-        }
+    const int rows_valid = nfoot - b * TB64;
+    if (words_ok) stage64_words(reinterpret_cast<const uint8_t *>(frame), a.pitch, a.H, a.W, Yb + b * TB64, X0, rows_valid, fill,
+                                s_in, G.pin, G.nwords, G.width, warp, lane);
+    else stage64_scalar<PixT>(frame, a.pitch, a.H, a.W, Yb + b * TB64, X0, rows_valid, fill, s_in, G.pin, G.width, warp, lane);
+    __syncthreads();
+    const int f = b * TB64 + lane;
+    if (warp * R64 < sw && f < nfoot) {
+        float2 acc[R64];
+        row_pass64(s_in + lane * G.pin + LPAD + G.w16 + warp * R64, wt, G.w16, acc);
+        // intermediate: [window][footprint row][strips·64] float2, 16-byte aligned groups of 8
+        float4 *dst = reinterpret_cast<float4 *>(a.mid + ((size_t)v * nfoot + f) * (size_t)(a.strips * SW64) + c0 + warp * R64);
+#pragma unroll
+        for (int j = 0; j < R64; j += 2) dst[j / 2] = make_float4(acc[j].x, acc[j].y, acc[j + 1].x, acc[j + 1].y);
     }
+}
+
+constexpr int PFC = 4;                   // batches of intermediate rows in flight ahead of the column pass
+
+// shared memory of dog_cols_wide: the fused kernel's ring + room for the batches in flight
+__host__ __device__ inline int cols_ring_rows(int L) { return geom64(L).nring + PFC * TB64; }
+
+template <int DELTA>
+__global__ void __launch_bounds__(THREADS64, 1)
+dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTaps wt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = a.L, w = a.w;
+    Geom64 G = geom64(L);
+    G.nring = cols_ring_rows(L);
+    float2 *s_ring = reinterpret_cast<float2 *>(smem_raw);               // [nring][RP64], slot = ring row mod nring
+    __shared__ unsigned long long s_best[WARPS64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int v, strip, chunk;
+    {
+        const int per_full = a.strips - 1, nc = (int)gridDim.x / a.strips;     // longest-first order, as the fused kernel
+        const int id = (int)blockIdx.x;
+        if (id < per_full * nc) { strip = id % per_full; const int r = id / per_full; chunk = r % a.chunks; v = r / a.chunks; }
+        else { strip = a.strips - 1; const int r = id - per_full * nc; chunk = r % a.chunks; v = r / a.chunks; }
+    }
+    int wy0, wx0;
+    if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
+    else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
+    const int c0 = strip * SW64;
+    const int r0 = chunk * a.CH;
+    const int ch = min(a.CH, a.wr - r0);
+    const int sw = min(SW64, a.wc - c0);
+    // Ring row f ↔ row r0 + f − pad of the window's footprint, pad chosen so that 2w + pad is a multiple of 32: the
+    // supports of output rows [32k, 32k + 32) of the chunk then complete with one batch (one column pass per 32 output
+    // rows instead of two partial ones).
+    const int pad = (TB64 - (2 * w) % TB64) % TB64;
+    const int nrows = ch + 2 * w + pad;    // ring rows of this chunk
+    const int nb = (nrows + TB64 - 1) / TB64;
+    const int nfw = a.wr + 2 * w;          // footprint rows of the window
+    const size_t mp = (size_t)(a.strips * SW64);
+    const float2 *mid = a.mid + (size_t)v * nfw * mp + c0;
+
+    // batch b of intermediate rows → ring, asynchronously (cp.async, 8 bytes: ring rows are 8-byte aligned); rows outside
+    // the window's footprint are zeros, as the fused kernel stages them
+    auto issue_batch = [&](int b) {
+#pragma unroll
+        for (int q = 0; q < TB64 / WARPS64; ++q) {
+            const int f = b * TB64 + warp + q * WARPS64;
+            const int fw = r0 + f - pad;                            // row of the window's footprint
+            float2 *dst = s_ring + (size_t)(f % G.nring) * RP64 + 2 * lane;
+            if (f < nrows && fw >= 0 && fw < nfw) {
+                const float2 *src = mid + (size_t)fw * mp + 2 * lane;
+                const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8u), "l"(src + 1) : "memory");
+            } else {
+                dst[0] = make_float2(0.f, 0.f); dst[1] = make_float2(0.f, 0.f);
+            }
+        }
+    };
+
+    float best_v = -INFINITY;
+    unsigned int best_i = 0xFFFFFFFFu;
+    for (int b = 0; b < PFC; ++b) {
+        if (b < nb) issue_batch(b);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int b = 0; b < nb; ++b) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(PFC - 1) : "memory");   // batch b has landed (this thread's copies)
+        __syncthreads();                     // … everybody's; and the column pass of batch b − 1 has finished reading
+        if (b + PFC < nb) issue_batch(b + PFC);      // overwrites ring rows older than anything batch b's pass reads
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        col_pass64<DELTA>(a, wt, G, s_ring, b, w, ch, sw, c0, r0, v, warp, lane, best_v, best_i, pad);
+    }
+    merge_and_publish64(a, v, wy0, wx0, best_v, best_i, s_best, tid, warp, lane);
 }
 
 int wide_max_kernel_len() { return kMaxLWide; }
 size_t wide_smem_bytes(int L) { return geom64(L).bytes; }
+size_t wide_cols_smem_bytes(int L) { return (size_t)cols_ring_rows(L) * RP64 * sizeof(float2); }
+// float2 elements of the two-phase intermediate of n windows
+size_t wide_mid_elems(int L, int wr, int wc, int n)
+{
+    const int strips = (wc + SW64 - 1) / SW64;
+    return (size_t)n * (size_t)(wr + 2 * (L / 2)) * (size_t)(strips * SW64);
+}
 
 cudaError_t wide_init_device()
 {
@@ -356,6 +513,10 @@ cudaError_t wide_init_device()
     PT_WIDE_OPTIN((dog_rect_argmax_wide<uint8_t, 4>))
     PT_WIDE_OPTIN((dog_rect_argmax_wide<float, 0>))
     PT_WIDE_OPTIN((dog_rect_argmax_wide<float, 4>))
+    PT_WIDE_OPTIN((dog_rows_wide<uint8_t>))
+    PT_WIDE_OPTIN((dog_rows_wide<float>))
+    PT_WIDE_OPTIN((dog_cols_wide<0>))
+    PT_WIDE_OPTIN((dog_cols_wide<4>))
 #undef PT_WIDE_OPTIN
     return cudaSuccess;
 }
@@ -373,6 +534,20 @@ cudaError_t launch_wide(const WinArgs &a, int n, int pixel, cudaStream_t s)
     auto at = [L](const float *t, int k) { return (k >= 0 && k < L) ? t[k] : 0.f; };
     for (int q = 0; q < kMaxLq16; ++q) wt.cq[q] = make_float4(at(cp, q), at(cp, q - 1), at(cm, q), at(cm, q - 1));
     for (int d = 0; d <= kMaxW16; ++d) wt.trow[d] = d <= w ? make_float2(rp[w + d], rm[w + d]) : make_float2(0.f, 0.f);
+    if (a.mid) {
+        // two-phase: every footprint batch row-filtered once, then the column pass per (chunk, strip)
+        const Geom64 G = geom64(L);
+        const int nbt = (a.wr + 2 * w + TB64 - 1) / TB64;
+        const size_t smem_rows = (size_t)TB64 * G.pin * sizeof(float), smem_cols = wide_cols_smem_bytes(L);
+        dim3 grid_rows((unsigned)(a.strips * nbt * n));
+        if (pixel == 0) dog_rows_wide<uint8_t><<<grid_rows, THREADS64, smem_rows, s>>>(a, wt);
+        else dog_rows_wide<float><<<grid_rows, THREADS64, smem_rows, s>>>(a, wt);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (delta == 0) dog_cols_wide<0><<<grid, THREADS64, smem_cols, s>>>(a, wt);
+        else dog_cols_wide<4><<<grid, THREADS64, smem_cols, s>>>(a, wt);
+        return cudaGetLastError();
+    }
     if (pixel == 0) {
         if (delta == 0) dog_rect_argmax_wide<uint8_t, 0><<<grid, THREADS64, smem, s>>>(a, wt);
         else dog_rect_argmax_wide<uint8_t, 4><<<grid, THREADS64, smem, s>>>(a, wt);

@@ -27,6 +27,7 @@ struct Cfg {
     int host_lanes = 0;       // host threads of the pageable footprint path, 0 = auto  (PT_HOST_LANES)
     int cluster = 0;          // lone-window cluster kernel: 0 auto, 1 off, 2/4/8 CTAs per window (PT_W45_CLUSTER)
     int wide = 1;             // 1: dog_rect_argmax_wide (64-column strips) where it fits, 0: always the 32-column kernel (PT_GENERIC_WIDE)
+    int two_phase = 1;        // wide kernel: 0 fused only, 1 auto, 2 always row pass and column pass as two launches (PT_WIDE_TWO_PHASE)
     int smem_optin = 0;       // largest dynamic shared memory per block the device allows (set at create)
     int bulk = 1;             // cluster kernel staging: 1 = one TMA tile copy per step into shared memory, 0 = global loads (PT_W45_BULK)
 };
@@ -67,6 +68,7 @@ struct WinArgs {
     unsigned int *xflag;       // [n] hand-off flags   } dog_window45_rot (windows hopping between SMs); zero between launches,
     int2 *xpos;                // [n] hand-off guesses } the kernel leaves them zeroed
     const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
+    float2 *mid;               // two-phase wide path: row-pass intermediate [n][wr + 2w][strips·64] (null = fused kernel)
 };
 
 // Orderable packing of (response, column-major index): max key = largest
@@ -120,6 +122,8 @@ cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s);
 // CTA (l up to ≈ 285), the 32-column kernel above covers longer kernels and narrow windows.
 int wide_max_kernel_len();
 size_t wide_smem_bytes(int L);
+size_t wide_cols_smem_bytes(int L);
+size_t wide_mid_elems(int L, int wr, int wc, int n);
 cudaError_t wide_init_device();
 cudaError_t launch_wide(const WinArgs &a, int n, int pixel, cudaStream_t s);
 

@@ -547,16 +547,20 @@ def test_wide_generic_kernel_equals_narrow_and_oracle(gpu_pkg, oracle, tw, ws, d
     fill = oracle.mode(f8)
     ref = oracle.step(f8, fill, tw, darker, ws, guess, dense=False, want_map=True)
     maps, outs = {}, {}
-    for wide in (1, 0):
+    # wide = 2: the two-phase variant of the 64-column kernel (dog_rows_wide + dog_cols_wide, row-pass intermediate in
+    # global memory); 1: the fused 64-column kernel; 0: the 32-column kernel
+    for wide in (1, 2, 0):
         for target in (592, 2000):                                   # 2000: more row chunks per strip
             trk = gpu_pkg.Tracker(frame, tw, ws, darker)
             try:
-                trk.set_option("wide", wide); trk.set_option("generic_target", target)
+                trk.set_option("window45", 0)                        # (l <= 65 would take the marching tile kernel)
+                trk.set_option("wide", min(wide, 1)); trk.set_option("generic_target", target)
+                trk.set_option("two_phase", 2 if wide == 2 else 0)
                 assert trk.fillvalue == fill
                 outs[wide, target] = (trk.step_resident(guess), trk.last_response)
                 maps[wide, target] = trk.response_map(guess)
                 name = trk._batch.last_kernel
-                assert name.startswith("dog_rect_argmax_wide" if wide else "dog_rect_argmax_generic"), name
+                assert name.startswith({1: "dog_rect_argmax_wide", 2: "dog_rows_wide", 0: "dog_rect_argmax_generic"}[wide]), name
             finally:
                 trk.close()
     base = maps[1, 592]

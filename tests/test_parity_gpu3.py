@@ -68,7 +68,7 @@ def test_small_geometries_through_the_window_kernels(gpu_pkg, oracle, synth, tw,
             elif name.startswith("C"):
                 assert b.last_kernel == f"dog_window45_cluster<{name[1]}>"
             else:
-                assert b.last_kernel.startswith("dog_rect_argmax")
+                assert b.last_kernel.startswith(("dog_rect_argmax", "dog_rows_wide"))
     ij0, r0 = results["per-SM"]
     for name in ("C2", "C4", "C8"):
         np.testing.assert_array_equal(results[name][0], ij0)
@@ -148,3 +148,36 @@ def test_small_geometry_host_paths_and_single_tracker(gpu_pkg, oracle, synth):
         if pin is not None:
             del av
             pin.close()
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_two_phase_wide_path_in_batches_and_host_lanes(gpu_pkg, oracle, synth, dtype):
+    """dog_rows_wide + dog_cols_wide (row-pass intermediate in global memory, one slice per window / per host lane):
+    a batch of chained resident steps and the pageable host-frame path (crops through the lanes) give the fused
+    kernel's results bit for bit and the oracle's positions; several row chunks per strip, windows over the frame edge."""
+    import torch
+    tw, ws, darker = 40, (73, 150), False
+    n, T, H, W = 5, 4, 220, 300
+    frames, start = make_case(synth, H, W, n, T, tw, darker, 900)
+    fr = frames if dtype is np.uint8 else frames.astype(np.float32) / np.float32(255.0)
+    dev = torch.from_numpy(fr).cuda()
+    out = {}
+    with gpu_pkg.TrackerBatch(n, (H, W), tw, ws, darker, dtype=dtype) as b:
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        fills = b.compute_fill()
+        for tp in (0, 2, 1):
+            b.set_option("two_phase", tp)
+            b.set_guess(start)
+            out["dev", tp] = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+            assert b.last_kernel.startswith("dog_rect_argmax_wide" if tp == 0 else "dog_rows_wide"), b.last_kernel
+            b.set_guess(start)
+            out["host", tp] = b.track_host([[fr[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+    for key, (ij, r) in out.items():
+        np.testing.assert_array_equal(ij, out["dev", 0][0], err_msg=str(key))
+        np.testing.assert_array_equal(r, out["dev", 0][1], err_msg=str(key))
+    ij0, r0 = out["dev", 0]
+    for v in range(n):
+        pos, resp, mx, near = oracle_chain(oracle, [frames[t, v] for t in range(T)], tw, darker, ws, start[v], int(fills[v]))
+        if near == 0:
+            np.testing.assert_array_equal(ij0[:, v], pos)
+        assert np.all(np.abs(r0[:, v] - resp) <= np.maximum(RTOL * mx, BLANK))

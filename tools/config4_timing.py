@@ -10,13 +10,14 @@ dev = torch.device("cuda", 0)
 f = np.full((H, W), 128, np.uint8)
 yy, xx = np.ogrid[0:H, 0:W]
 f[(yy - 1000) ** 2 + (xx - 2000) ** 2 <= 2500] = 255
-cases = [(n, ws, wide) for n in (1, 16, 64) for ws in (173, 401) for wide in (1, 0)]
+# wide: 0 = 32-column kernel, 1 = fused 64-column kernel, 2 = 64-column kernel in two phases, 3 = automatic choice
+cases = [(n, ws, wide) for n in (1, 4, 16, 64) for ws in (173, 401) for wide in (3, 2, 1, 0)]
 if len(sys.argv) == 4:                      # one case: n ws wide   (for ncu)
     cases = [tuple(int(x) for x in sys.argv[1:4])]
 for n, ws, wide in cases:
     if True:
         b = pkg.TrackerBatch(n, (H, W), 100, (ws, ws), False)
-        b.set_option("wide", wide)
+        b.set_option("wide", min(wide, 1)); b.set_option("two_phase", {0: 0, 1: 0, 2: 2, 3: 1}[wide])
         b.set_frames([f] * n); b.set_fill(128)
         ext = torch.cuda.ExternalStream(b.stream, device=dev)
         g = np.tile([1010, 1990], (n, 1))
