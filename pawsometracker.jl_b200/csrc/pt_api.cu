@@ -389,13 +389,14 @@ void decompose(pt::WinArgs &a, int nwin, int target)
 }
 
 // Row chunks of the column-pass launch of the two-phase wide path.  Chunks cost no arithmetic here, only a re-read of
-// 2w intermediate rows from L2 each; a CTA's cost ≈ copies (≈ 150 cycles per 32 rows, asynchronous) + column pass (32·Lq16 cycles per
+// 2w intermediate rows from L2 each; a CTA's cost ≈ copies (≈ 1000 cycles per 32 rows = 16 KB when every SM pulls from L2:
+// 64 windows of 401x401 in 32-row chunks moved 859 MB and took 410 µs) + column pass (32·Lq16 cycles per
 // 32 output rows), CTAs are uniform, so the launch costs whole waves of them.
 void decompose_cols(pt::WinArgs &a, int nwin, int sms)
 {
     a.strips = (a.wc + 2 * pt::kTileCols - 1) / (2 * pt::kTileCols);
     const int nbo = (a.wr + pt::kBatchRows - 1) / pt::kBatchRows;
-    const double colc = 32.0 * (double)(((a.L + 1 + 15) / 16) * 16), cpy = 150.0;
+    const double colc = 32.0 * (double)(((a.L + 1 + 15) / 16) * 16), cpy = 1000.0;
     double best = 1e300;
     int best_k = 1;
     for (int k = 1; k <= nbo; ++k) {
