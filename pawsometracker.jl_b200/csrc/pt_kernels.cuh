@@ -68,6 +68,7 @@ struct WinArgs {
     unsigned int *xflag;       // [n] hand-off flags   } dog_window45_rot (windows hopping between SMs); zero between launches,
     int2 *xpos;                // [n] hand-off guesses } the kernel leaves them zeroed
     const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
+    int host_frames;           // frames/strides address page-locked HOST memory (zero-copy over PCIe): changes the cluster policy only
     float2 *mid;               // two-phase wide path: row-pass intermediate [n][wr + 2w][strips·64] (null = fused kernel)
 };
 

@@ -94,6 +94,7 @@ struct Args45 {
     int rr, rc, wr, wc;
     int f_lo, nfr, ng, cs;
     unsigned int inv_nfr;
+    int host_frames;                    // frames are page-locked host memory (policy only)
     int skew;                           // 1: alternate the row passes of the two windows of a CTA (token); 2: lock
     int tm_rows_step, tm_rows_frame;    // dog_window45_cluster, TMA tensor mode: rows of the 2-D frame tensor per step / per video
     unsigned int *xflag;                // [n] hand-off flags of dog_window45_rot (zero between launches)
@@ -1273,6 +1274,12 @@ static int cluster_size_for(const WinArgs &a, const Cfg &cfg, int n)
     if (cfg.cluster == 1) return 1;
     if (cfg.cluster == 2 || cfg.cluster == 4 || cfg.cluster == 8) return cfg.cluster;
     const int sms = cfg.sms;
+    if (a.host_frames) {
+        // page-locked host frames at regular strides (zero-copy over PCIe, region prefetched one step ahead), measured
+        // with tools/pinned_chain_timing.py, µs per frame: n = 1: 4.2 (2 or 4 CTAs, TMA) vs 7.5 per-SM; n = 4: 6.2-6.7 vs 7.5;
+        // n = 8: 6.6 (2 CTAs, global loads) vs 7.7; n = 16: per-SM 9.0 vs 22-26 (the slices' redundant rows cost PCIe bytes)
+        return n <= 8 ? 2 : 1;
+    }
     if (a.frame_ptrs) {
         // zero-copy host frames: every CTA of a cluster pulls its own slice rows over PCIe (C = 4: 3.5x the bytes of
         // one footprint), which is free for a handful of windows and costs bandwidth for many
@@ -1354,7 +1361,8 @@ static cudaError_t launch_cluster(const Args45 &k, const Taps45 &tp, const Cfg &
     const bool aligned16 = pixel == 0 && !k.frame_ptrs &&
                            ((reinterpret_cast<uintptr_t>(k.frames) | (uintptr_t)k.pitch | (uintptr_t)k.frame_stride |
                              (uintptr_t)k.step_stride) & 15u) == 0;
-    const int use_bulk = (cfg.bulk && aligned16) ? 1 : 0;              // the TMA path needs 16-byte aligned rows
+    // the TMA path needs 16-byte aligned rows; over PCIe (host frames) its 153-row regions pay off for one or two windows only
+    const int use_bulk = (cfg.bulk && aligned16 && !(k.host_frames && k.n > 2)) ? 1 : 0;
     if (pixel == 0) {
         if (C == 2) return launch_cluster_t<uint8_t, 2>(k, tp, use_bulk, s);
         if (C == 4) return launch_cluster_t<uint8_t, 4>(k, tp, use_bulk, s);
@@ -1489,6 +1497,7 @@ cudaError_t launch_window45(const WinArgs &a, const Cfg &cfg, int n, int pixel, 
 #ifdef PT_PROBES
     k.dbg = g_dbg;
 #endif
+    k.host_frames = a.host_frames;
     k.rr = a.rr; k.rc = a.rc; k.wr = a.wr; k.wc = a.wc;
     k.f_lo = HW - a.L / 2;                                  // first footprint row that meets a non-zero tap
     k.nfr = a.wr + 2 * (a.L / 2);

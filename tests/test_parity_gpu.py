@@ -423,8 +423,17 @@ def test_zero_copy_pinned_host_frames(gpu_pkg, oracle, synth):
         lc = b.launch_count
         ij_zc, r_zc = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
         assert b.launch_count - lc == 1, "pinned frames must take the single-launch zero-copy path"
-        assert b.last_kernel == "dog_window45_cluster<4>"              # 5 videos: lone-window kernel, zero-copy rows
+        # 5 videos at regular strides in one page-locked buffer: handed over as base + strides (region prefetch one step
+        # ahead), lone-window kernel with 2 CTAs per window
+        assert b.last_kernel == "dog_window45_cluster<2>"
         nxt, _ = b.step(None)                                          # chain state was left on the device
+        # the same frames in an order that is NOT a regular stride pattern: frame-pointer table, 4 CTAs per window
+        perm = [3, 0, 4, 1, 2]                                         # (every video has the same fill value, 128)
+        b.set_guess(start)
+        ij_tab, r_tab = b.track_host([[pnp[t, perm[v]] for v in range(n)] for t in range(T)], mode="footprint")
+        assert b.last_kernel == "dog_window45_cluster<4>"
+        np.testing.assert_array_equal(ij_tab, ij_zc[:, perm])
+        np.testing.assert_array_equal(r_tab, r_zc[:, perm])
         b.set_option("cluster", 1)                                     # the same through the per-SM kernel
         b.set_guess(start)
         ij_ll, r_ll = b.track_host([[pnp[t, v] for v in range(n)] for t in range(T)], mode="footprint")
