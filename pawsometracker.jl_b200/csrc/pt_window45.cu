@@ -227,6 +227,7 @@ __device__ __forceinline__ void stage_rows_u8(const uint8_t *frame, int pitch, i
         const int Y = fy0 + f;
         const bool ok = wordok && (f < NROWS) && (f >= f_lo) && (f < f_hi) && (kInterior || ((Y >= 0) && (Y < H)));
         wd[r] = fillw;
+        // (an L2::64B prefetch-size hint on this load does not change the PCIe traffic of zero-copy host frames: measured)
         if (ok) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(wd[r]) : "l"(addr));
         addr += rstep;                                       // one 64-bit add per load
     }
