@@ -429,11 +429,21 @@ def run_gpu(args, ranks):
     if True:
         rep = 0
         while True:
+            # The ranks meet BEFORE the untimed part (flush + warm-up steps, ≈ 0.15 ms of GPU work), not between it and
+            # the timed launch: a barrier there leaves every GPU idle for its latency, and a GPU that sat idle runs the
+            # timed launch slower (see --idle-ms).  The timed region is still bracketed by barrier + synchronize.
+            ranks.barrier()
             benchlib.flush_l2(flush.data_ptr(), flush.numel(), batch.stream)      # untimed: cold L2 for every repeat
             batch.set_guess(pos[0])
             run_chain(0, Wm)                                                         # warm-up steps (untimed)
-            ranks.barrier()
             torch.cuda.synchronize(device)
+            if args.idle_ms > 0:
+                # diagnostic (weak-scaling analysis): a GPU that sat idle before the timed launch runs it slower — 0.2 ms
+                # idle: +2.4 µs per 20-step launch, 1 ms: +4.7, 5 ms: +6.1 (0.1834 → 0.1895 ms).  In a multi-rank run the
+                # barrier and the reductions between repeats leave every rank idle for about a millisecond, which is the
+                # whole per-rank loss of the weak-scaling runs (0.188-0.190 ms on every rank; two independent single-GPU
+                # processes running at once: 0.1833 / 0.1843).
+                time.sleep(args.idle_ms * 1e-3)
             lc0 = batch.launch_count
             # EXACTLY K timed steps: CUDA event, the chained launch(es), CUDA event on the batch's stream, issued back
             # to back from C (ptb_time_chain) so that no interpreter time sits between the first event and the launch
@@ -477,10 +487,10 @@ def run_gpu(args, ranks):
         ok_s = bool(np.array_equal(chk_s, truth_for_steps(pos, min(Wm + K, slots))[:, :ns]))
         ms_s, loc_s = [], []
         for _ in range(12):
+            ranks.barrier()
             benchlib.flush_l2(flush.data_ptr(), flush.numel(), bs.stream)
             bs.set_guess(pos[0][:ns])
             chain_s(0, Wm)
-            ranks.barrier()
             torch.cuda.synchronize(device)
             ms_rep = benchlib.time_chain(pkg.lib, bs, chain_segments(Wm % slots, K), step_stride, frame_stride, W, bs.stream)
             torch.cuda.synchronize(device)
@@ -741,7 +751,7 @@ def run_gpu(args, ranks):
                 "config": dict(workload_config(args.scaling, world), repeats=len(reps_ms),
                                l2="inputs larger than L2: each timed step reads a step-slot (531 MB) untouched "
                                   f"since the previous repeat; ring of {slots} slots; L2 flushed between repeats",
-                               timing="CUDA events on the launching stream, the event pair and the chained launch issued back to back from C (ptb_time_chain of libpawsome_bench.so), barrier + synchronize on both sides, median over repeats, max over ranks"),
+                               timing="CUDA events on the launching stream, the event pair and the chained launch issued back to back from C (ptb_time_chain of libpawsome_bench.so), ranks meet at a barrier before the untimed flush + warm-up steps, synchronize, K timed steps, synchronize + barrier; median over repeats, max over ranks"),
                 "clocks": clocks, "e2e": e2e, "e2e_frames": e2e_frames, "roofline": roofline,
                 "cpu_baseline": cpu, "fullframe_dog": fullframe, "balanced_batch": balanced, "mode_fill": mode_fill,
                 "strong": strong_obj, "ms_K_per_rank": ms_K_per_rank,
@@ -771,6 +781,7 @@ def main():
                     help="weak: 256 videos per GPU (default); strong: 256 videos in total, video_id mod world "
                          "(BASELINE configs[2] as written)")
     ap.add_argument("--no-strong", action="store_true", help="skip the supplementary strong-scaling measurement (N > 1)")
+    ap.add_argument("--idle-ms", type=float, default=0.0, help="diagnostic: host sleep between the synchronise and the timed launch")
     ap.add_argument("--no-pcie", action="store_true", help="skip the NVML PCIe RX measurement of the e2e path")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
