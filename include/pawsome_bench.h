@@ -29,7 +29,8 @@ PTB_API int ptb_probe_ffma2_issue(int device, int na, double *ms_out);
 /* Overwrite `bytes` of device scratch on `stream` (L2 flush between timed repeats). */
 PTB_API int ptb_flush_l2(void *scratch, size_t bytes, void *stream);
 
-/* Device time (ms, CUDA events on `stream`) of a chain of pt_batch_track_device_async calls issued from C: event,
+/* Device time (ms, CUDA events on `stream`) of a chain of pt_batch_track_device_async calls issued from C: device-wide
+ * synchronise, event,
  * nseg calls (track_fn = address of pt_batch_track_device_async of the loaded product library; segment s tracks Ts[s]
  * steps from bases[s]), event, wait for the second event.  Issuing the three from C keeps interpreter time between
  * the first event and the launch out of the device-timed region (with an idle GPU the first event completes at once

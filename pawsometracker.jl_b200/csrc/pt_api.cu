@@ -202,6 +202,7 @@ const pt::Cfg &defaults_from_env()
         cfg.window45 = getenv("PT_DISABLE_WINDOW45") ? 0 : 1;
         cfg.rect45 = getenv("PT_DISABLE_RECT45") ? 0 : 1;
         cfg.rot = geti("PT_W45_ROT", 1);
+        cfg.rot_stride = std::max(0, geti("PT_W45_ROT_STRIDE", 0));
         cfg.skew = geti("PT_W45_SKEW", 1);
         cfg.r45_chunks = std::max(0, geti("PT_R45_CHUNKS", 0));
         cfg.generic_target = std::max(1, geti("PT_GENERIC_TARGET", 4 * 148));
@@ -1304,7 +1305,7 @@ int pt_batch_set_option(pt_batch *b, const char *name, int value)
     struct Opt { const char *name; int pt::Cfg::* field; int lo, hi; };
     static const Opt opts[] = {
         {"window45", &pt::Cfg::window45, 0, 1},       {"rect45", &pt::Cfg::rect45, 0, 1},
-        {"rot", &pt::Cfg::rot, 0, 3},                 {"skew", &pt::Cfg::skew, 0, 2},
+        {"rot", &pt::Cfg::rot, 0, 3},                 {"rot_stride", &pt::Cfg::rot_stride, 0, 1 << 20},                 {"skew", &pt::Cfg::skew, 0, 2},
         {"r45_chunks", &pt::Cfg::r45_chunks, 0, 1 << 20}, {"generic_target", &pt::Cfg::generic_target, 1, 1 << 20},
         {"mode_slow", &pt::Cfg::mode_slow, 0, 1},     {"zero_copy", &pt::Cfg::zero_copy, 0, 1},
         {"host_lanes", &pt::Cfg::host_lanes, 0, 1024}, {"cluster", &pt::Cfg::cluster, 0, 8},

@@ -213,6 +213,9 @@ PTB_API int ptb_time_chain(void *track_fn, void *batch, int nseg, const void *co
     cudaEvent_t e0, e1;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -2;
     int rc = 0;
+    // the device-wide synchronise that brackets the timed region, issued here so that the launch follows it within
+    // microseconds (a GPU that sat idle runs the first microseconds of the next kernel slower: bench.py --idle-ms)
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return -2; }
     cudaEventRecord(e0, s);
     for (int i = 0; i < nseg && rc == 0; ++i) rc = fn(batch, bases[i], step_stride, frame_stride, pitch, Ts[i], stream);
     cudaEventRecord(e1, s);

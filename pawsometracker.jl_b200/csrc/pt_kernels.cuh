@@ -19,6 +19,7 @@ struct Cfg {
     int window45 = 1;         // 0: never use the l = 65 / 45x45 specialised kernels   (PT_DISABLE_WINDOW45)
     int rect45 = 1;           // 0: never use dog_rect45_march                          (PT_DISABLE_RECT45)
     int rot = 1;              // dog_window45_rot: 0 off, 1 where it pays, 2 always     (PT_W45_ROT)
+    int rot_stride = 0;       // slots the empty arc advances per step, 0 = its own length (PT_W45_ROT_STRIDE)
     int skew = 1;             // two-window CTAs: 0 free-running, 1 token, 2 lock       (PT_W45_SKEW)
     int r45_chunks = 0;       // chunks per strip of dog_rect45_march, 0 = cost model   (PT_R45_CHUNKS)
     int generic_target = 592; // CTAs the generic kernel aims for                       (PT_GENERIC_TARGET)

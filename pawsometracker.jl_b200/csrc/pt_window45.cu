@@ -95,6 +95,7 @@ struct Args45 {
     int f_lo, nfr, ng, cs;
     unsigned int inv_nfr;
     int host_frames;                    // frames are page-locked host memory (policy only)
+    int rstride;                        // dog_window45_rot: slots the empty arc advances per step (0 = its own length)
     int skew;                           // 1: alternate the row passes of the two windows of a CTA (token); 2: lock
     int tm_rows_step, tm_rows_frame;    // dog_window45_cluster, TMA tensor mode: rows of the 2-D frame tensor per step / per video
     unsigned int *xflag;                // [n] hand-off flags of dog_window45_rot (zero between launches)
@@ -676,15 +677,17 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
     int2 g = make_int2(0, 0);
     float fill = 0.f;
     // (nh·t) mod R and (nh·t) mod m for the current step and the next one, advanced by additions (nh < m < R)
-    int remR = 0, remM = 0, remR1 = nh, remM1 = nh;
+    // the arc of empty slots advances by `adv` slots per step (≤ its own length nh): adv windows hop per step
+    const int adv = (a.rstride > 0 && a.rstride < nh) ? a.rstride : nh;
+    int remR = 0, remM = 0, remR1 = adv, remM1 = adv;
     int v_next = rot_window_rem(slot, 0, 0, R, m);
     for (int t = 0; t < a.T; ++t) {
         const unsigned int it = (unsigned int)t;
         const int v = v_next;
         v_next = rot_window_rem(slot, remR1, remM1, R, m);          // holder of this slot at step t + 1
         remR = remR1; remM = remM1;
-        remR1 += nh; if (remR1 >= R) remR1 -= R;
-        remM1 += nh; if (remM1 >= m) remM1 -= m;
+        remR1 += adv; if (remR1 >= R) remR1 -= R;
+        remM1 += adv; if (remM1 >= m) remM1 -= m;
         if (v < 0) { prev_v = -1; continue; }
         if (v != prev_v) {
             fill = a.fill[v];
@@ -1499,6 +1502,7 @@ cudaError_t launch_window45(const WinArgs &a, const Cfg &cfg, int n, int pixel, 
     k.dbg = g_dbg;
 #endif
     k.host_frames = a.host_frames;
+    k.rstride = cfg.rot_stride;
     k.rr = a.rr; k.rc = a.rc; k.wr = a.wr; k.wc = a.wc;
     k.f_lo = HW - a.L / 2;                                  // first footprint row that meets a non-zero tap
     k.nfr = a.wr + 2 * (a.L / 2);

@@ -315,7 +315,7 @@ class Tracker:
         pitches = {_check_frame(f, self.sz[0], self.sz[1], self._batch.pixel) for f in frames}
         if len(pitches) != 1:
             raise ValueError("all frames of a chunk must share one pitch")
-        ptrs = (C.c_void_p * T)(*[f.ctypes.data for f in frames])
+        ptrs = (C.c_void_p * T)(*[f.__array_interface__["data"][0] for f in frames])
         g = (C.c_int32 * 2)(int(guess[0]), int(guess[1]))
         out = np.empty((T, 2), np.int32)
         resp = np.empty(T, np.float32)

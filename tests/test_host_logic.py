@@ -102,3 +102,44 @@ def test_segment_chains_split_at_explicit_start_locations(pkg):
     assert [[seg[0] for seg in c] for c in chains] == [[0, 1], [2, 3], [4], [5]]
     assert chains[0][0][4] is None and chains[1][0][4] == pkg.CartesianIndex(5, 6) and chains[1][1][4] is None
     assert [len(c) for c in pkg.split_chains(files, [0.0] * 6, [1.0] * 6, [None] * 6)] == [6]
+
+
+def test_track_chunks_frame_order_for_every_kind_of_source(pkg, monkeypatch):
+    """api._track_chunks (the chunked frame loop of track_one, src/PawsomeTracker.jl:163-169): sources that hand frames
+    out by reference, sources that decode into the page-locked ring, and sources that switch between the two — every frame
+    reaches the tracker exactly once and in order (host logic only: fake tracker, no device)."""
+    import sys
+    api = sys.modules[pkg.__name__ + ".api"]
+
+    class FakePinned:
+        def __init__(self, shape, dtype): self.array = np.zeros(shape, dtype)
+        def close(self): pass
+
+    monkeypatch.setattr(api, "PinnedArray", FakePinned)
+
+    class FakeTrk:
+        sz = (4, 6); img = np.zeros((4, 6), np.uint8)
+        def track_frames(self, frames, guess):
+            assert 1 <= len(frames) <= api.CHUNK_FRAMES_REF
+            return np.array([[int(f[0, 0]), len(frames)] for f in frames], np.int32), None
+
+    class Src:
+        def __init__(self, n, by_ref): self.n, self.k, self.by_ref = n, 0, by_ref
+        def eof(self): return self.k >= self.n
+        def read_ref(self):
+            if self.by_ref(self.k):
+                f = np.full((4, 6), self.k % 251, np.uint8); self.k += 1
+                return f
+            return None
+        def read(self, out=None):
+            out[...] = self.k % 251; self.k += 1
+            return out
+
+    for by_ref in (lambda k: True, lambda k: False, lambda k: k < 100, lambda k: k % 2 == 0, lambda k: k > 70):
+        for n in (1, 5, 64, 65, 300, 700):
+            ind = [(0, 0)]
+            api._track_chunks(FakeTrk(), Src(n, by_ref), n + 1, ind)
+            assert [a for a, _ in ind[1:]] == [k % 251 for k in range(n)]
+            ind = [(0, 0)]
+            api._track_chunks(FakeTrk(), Src(n, by_ref), min(n, 40) + 1, ind)      # stop before the source ends
+            assert [a for a, _ in ind[1:]] == [k % 251 for k in range(min(n, 40))]
