@@ -355,7 +355,10 @@ __device__ __forceinline__ void convert_rows_u8(const uint8_t *raw, int raw_y0, 
 // ---- row pass over one staged 109×109 tile: item = (footprint row f, group gq of 5 output columns);
 // lanes walk rows.  One FADD (symmetric fold) feeds one packed FFMA2 advancing (narrow, wide).
 // NROWS rows of s_in (from row 0) → NROWS rows of s_mid (from the pointer given).
-__device__ __forceinline__ void row_item45(const float *row, float2 *dst, const Taps45 &tp)
+// kSkip (kernels shorter than 65): the taps beyond the kernel's half width w are zero — the unrolled tap loop leaves at
+// d = 9, 17 or 25 when nothing but zeros follows (one uniform branch per 8 taps).
+template <bool kSkip = false>
+__device__ __forceinline__ void row_item45(const float *row, float2 *dst, const Taps45 &tp, int w = HW)
 {
     float x[RR + 2 * HW];
 #pragma unroll
@@ -365,6 +368,7 @@ __device__ __forceinline__ void row_item45(const float *row, float2 *dst, const 
     for (int j = 0; j < RR; ++j) acc[j] = fmul2(make_float2(x[j + HW], x[j + HW]), tp.rt[0]);
 #pragma unroll
     for (int d = 1; d <= HW; ++d) {
+        if (kSkip && (d & 7) == 1 && d > 1 && d > w) break;
 #pragma unroll
         for (int j = 0; j < RR; ++j) {
             const float s = x[j + HW - d] + x[j + HW + d];   // exact for u8 frames (integers)
@@ -387,6 +391,7 @@ __device__ __forceinline__ void row_pass45(const float *s_in, float2 *s_mid, int
 
 // The same over the footprint rows [f_lo, f_lo + nfr) and the first ng column groups only (windows smaller than
 // 45×45 / kernels shorter than 65: the other rows meet zero taps only, the other columns are masked).
+template <bool kSkip>
 __device__ __forceinline__ void row_pass45_rt(const float *s_in, float2 *s_mid, int tid, const Taps45 &tp,
                                               int f_lo, int nfr, int ng, unsigned int inv_nfr)
 {
@@ -394,7 +399,7 @@ __device__ __forceinline__ void row_pass45_rt(const float *s_in, float2 *s_mid, 
 #pragma unroll 1
     for (int item = tid; item < nitems; item += THREADS) {
         const int gq = (int)(((unsigned int)item * inv_nfr) >> 18), f = f_lo + item - gq * nfr;
-        row_item45(s_in + f * PIN + gq * RR, s_mid + f * PM + gq * RR, tp);
+        row_item45<kSkip>(s_in + f * PIN + gq * RR, s_mid + f * PM + gq * RR, tp, HW - f_lo);
     }
 }
 
@@ -403,8 +408,12 @@ __device__ __forceinline__ void row_pass45_rt(const float *s_in, float2 *s_mid, 
 // parts accumulate separately (10 independent dependency chains).  The tile sits at (gy0, gx0) inside an
 // output rectangle of wr_tot × wc_tot: outputs beyond it are masked, the key carries the rectangle's
 // column-major index.  map_out (optional) receives the responses, row-major with pitch wc_tot.
+// kSkip (kernels shorter than 65, i_lo = 32 − w): intermediate rows i < i_lo and i > 72 − i_lo of a thread's column meet
+// zero taps only — they are skipped in chunks of 8 (one uniform branch per chunk).
+template <bool kSkip = false>
 __device__ __forceinline__ unsigned long long col_pass45(const float2 *s_mid, int tid, const Taps45 &tp,
-                                                         int gy0, int gx0, int wr_tot, int wc_tot, float *map_out, int cs = 48)
+                                                         int gy0, int gx0, int wr_tot, int wc_tot, float *map_out, int cs = 48,
+                                                         int i_lo = 0)
 {
     // items are laid out cs = 48 (32, 16 for narrow windows) per row group: a half-warp — the unit of a 64-bit
     // shared-memory access — never straddles two row groups, whose addresses differ by an odd multiple of the pitch
@@ -416,23 +425,31 @@ __device__ __forceinline__ unsigned long long col_pass45(const float2 *s_mid, in
     float acc8p = 0.f, acc8m = 0.f;
 #pragma unroll
     for (int p = 0; p < R / 2; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
+    const int i_hi = R + 2 * HW - 1 - i_lo;           // last row that meets a non-zero tap (row i meets taps i − 8 … i)
 #pragma unroll
-    for (int i = 0; i < R + 2 * HW; ++i) {
-        const float2 m = col[i * PM];
+    for (int c8 = 0; c8 < (R + 2 * HW + 7) / 8; ++c8) {
+        if (kSkip && (8 * c8 + 8 <= i_lo || 8 * c8 > i_hi)) continue;
 #pragma unroll
-        for (int p = 0; p < R / 2; ++p) {
-            const int q = i - 2 * p;                 // tap of the even output; the odd one uses q-1
-            if (q >= 0 && q <= L) accP[p] = ffma2(make_float2(m.x, m.x), tp.cpp[q], accP[p]);
-        }
+        for (int ii = 0; ii < 8; ++ii) {
+            const int i = 8 * c8 + ii;
+            if (i < R + 2 * HW) {
+                const float2 m = col[i * PM];
 #pragma unroll
-        for (int p = 0; p < R / 2; ++p) {
-            const int q = i - 2 * p;
-            if (q >= 0 && q <= L) accM[p] = ffma2(make_float2(m.y, m.y), tp.cmq[q], accM[p]);
-        }
-        const int q8 = i - (R - 1);
-        if (q8 >= 0 && q8 < L) {
-            acc8p = fmaf(m.x, tp.cpp[q8].x, acc8p);
-            acc8m = fmaf(m.y, tp.cmq[q8].x, acc8m);
+                for (int p = 0; p < R / 2; ++p) {
+                    const int q = i - 2 * p;                 // tap of the even output; the odd one uses q-1
+                    if (q >= 0 && q <= L) accP[p] = ffma2(make_float2(m.x, m.x), tp.cpp[q], accP[p]);
+                }
+#pragma unroll
+                for (int p = 0; p < R / 2; ++p) {
+                    const int q = i - 2 * p;
+                    if (q >= 0 && q <= L) accM[p] = ffma2(make_float2(m.y, m.y), tp.cmq[q], accM[p]);
+                }
+                const int q8 = i - (R - 1);
+                if (q8 >= 0 && q8 < L) {
+                    acc8p = fmaf(m.x, tp.cpp[q8].x, acc8p);
+                    acc8m = fmaf(m.y, tp.cmq[q8].x, acc8m);
+                }
+            }
         }
     }
     float acc[R];
@@ -460,12 +477,15 @@ __device__ __forceinline__ void bar_half(int half)
     asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(THREADS) : "memory");
 }
 
-// kFull: the default geometry (l = 65, 45×45 window) with every bound a compile-time constant; !kFull: any shorter
-// kernel / smaller window, bounds from Args45 (see there).
-template <typename PixT, bool kFull>
+// kGeom 0: the default geometry (l = 65, 45×45 window) with every bound a compile-time constant; 1: any shorter kernel /
+// smaller window, bounds from Args45 (see there); 2: the same for kernels of half width ≤ 24, with the tap loops leaving
+// in chunks of 8 where only zero taps follow (tw ≤ 18: 7-16 % faster; with longer kernels nothing is skipped and the
+// exits cost 4-6 %, hence a separate instantiation).
+template <typename PixT, int kGeom>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Taps45 tp)
 {
+    constexpr bool kFull = kGeom == 0, kSkip = kGeom == 2;
     const int g_rr = kFull ? WR / 2 : a.rr, g_rc = kFull ? WC / 2 : a.rc, g_wr = kFull ? WR : a.wr, g_wc = kFull ? WC : a.wc;
     const int g_flo = kFull ? 0 : a.f_lo, g_nfr = kFull ? FR : a.nfr, g_cs = kFull ? 48 : a.cs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -553,7 +573,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         }
 
         if (kFull) row_pass45<FR>(s_in, s_mid, tid, tp);
-        else row_pass45_rt(s_in, s_mid, tid, tp, a.f_lo, a.nfr, a.ng, a.inv_nfr);
+        else row_pass45_rt<kSkip>(s_in, s_mid, tid, tp, a.f_lo, a.nfr, a.ng, a.inv_nfr);
         bar_half(half);
         if (locked && tid == 0) atomicExch(&s_rowlock, 0);
         if (tokens) {                                          // hand the row-pass token to the other window
@@ -563,7 +583,7 @@ dog_window45_argmax(const __grid_constant__ Args45 a, const __grid_constant__ Ta
         ++round;
         PT_PROBE(3, tid);
 
-        const unsigned long long key = warp_max_key(col_pass45(s_mid, tid, tp, 0, 0, g_wr, g_wc, nullptr, g_cs));
+        const unsigned long long key = warp_max_key(col_pass45<kSkip>(s_mid, tid, tp, 0, 0, g_wr, g_wc, nullptr, g_cs, g_flo));
         if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
         bar_half(half);
         PT_PROBE(4, tid);
@@ -636,10 +656,11 @@ __device__ __forceinline__ int rot_window_rem(int slot, int remR, int remM, int 
     return u;
 }
 
-template <typename PixT, bool kFull>
+template <typename PixT, int kGeom>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps45 tp)
 {
+    constexpr bool kFull = kGeom == 0, kSkip = kGeom == 2;
     const int g_rr = kFull ? WR / 2 : a.rr, g_rc = kFull ? WC / 2 : a.rc, g_wr = kFull ? WR : a.wr, g_wc = kFull ? WC : a.wc;
     const int g_flo = kFull ? 0 : a.f_lo, g_nfr = kFull ? FR : a.nfr, g_cs = kFull ? 48 : a.cs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -744,12 +765,12 @@ dog_window45_rot(const __grid_constant__ Args45 a, const __grid_constant__ Taps4
         PT_PROBE(2, tid);
 
         if (kFull) row_pass45<FR>(s_in, s_mid, tid, tp);
-        else row_pass45_rt(s_in, s_mid, tid, tp, a.f_lo, a.nfr, a.ng, a.inv_nfr);
+        else row_pass45_rt<kSkip>(s_in, s_mid, tid, tp, a.f_lo, a.nfr, a.ng, a.inv_nfr);
         bar_half(half);
         if (tid == 0) atomicExch(&s_rowlock, 0);
         PT_PROBE(3, tid);
 
-        const unsigned long long key = warp_max_key(col_pass45(s_mid, tid, tp, 0, 0, g_wr, g_wc, nullptr, g_cs));
+        const unsigned long long key = warp_max_key(col_pass45<kSkip>(s_mid, tid, tp, 0, 0, g_wr, g_wc, nullptr, g_cs, g_flo));
         if (lane == 0) s_key[(it & 1) * NWARPS + warp] = key;
         bar_half(half);
         PT_PROBE(4, tid);
@@ -1449,14 +1470,13 @@ cudaError_t window45_init_device()
 #define PT_OPTIN(k, bytes)                                                                      \
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));       \
     if (e != cudaSuccess) return e;
-    PT_OPTIN((dog_window45_argmax<uint8_t, true>), smem)
-    PT_OPTIN((dog_window45_argmax<float, true>), smem)
-    PT_OPTIN((dog_window45_rot<uint8_t, true>), smem)
-    PT_OPTIN((dog_window45_rot<float, true>), smem)
-    PT_OPTIN((dog_window45_argmax<uint8_t, false>), smem)
-    PT_OPTIN((dog_window45_argmax<float, false>), smem)
-    PT_OPTIN((dog_window45_rot<uint8_t, false>), smem)
-    PT_OPTIN((dog_window45_rot<float, false>), smem)
+#define PT_OPTIN_G(G)                                      \
+    PT_OPTIN((dog_window45_argmax<uint8_t, G>), smem)      \
+    PT_OPTIN((dog_window45_argmax<float, G>), smem)        \
+    PT_OPTIN((dog_window45_rot<uint8_t, G>), smem)         \
+    PT_OPTIN((dog_window45_rot<float, G>), smem)
+    PT_OPTIN_G(0) PT_OPTIN_G(1) PT_OPTIN_G(2)
+#undef PT_OPTIN_G
     PT_OPTIN(dog_rect45_march<uint8_t>, smem)
     PT_OPTIN(dog_rect45_march<float>, smem)
     PT_CLUSTER_OPTINS
@@ -1522,24 +1542,30 @@ cudaError_t launch_window45(const WinArgs &a, const Cfg &cfg, int n, int pixel, 
     // one CTA per SM, two windows per CTA; with n ≤ #SMs every window gets its own SM
     const int grid = std::min(sms, n);
     const size_t smem = 2 * HALF_SMEM;
-    const bool full = full_geometry(k);
+    const int geom = full_geometry(k) ? 0 : (a.L / 2 <= 24 ? 2 : 1);      // see dog_window45_argmax
     if (uses_rot(a, cfg, n)) {
         // plain launch: the CTAs establish co-residency themselves and fall back to the static schedule otherwise
-        if (full) {
-            if (pixel == 0) dog_window45_rot<uint8_t, true><<<grid, CTA_THREADS, smem, s>>>(k, tp);
-            else dog_window45_rot<float, true><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        if (geom == 0) {
+            if (pixel == 0) dog_window45_rot<uint8_t, 0><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+            else dog_window45_rot<float, 0><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        } else if (geom == 1) {
+            if (pixel == 0) dog_window45_rot<uint8_t, 1><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+            else dog_window45_rot<float, 1><<<grid, CTA_THREADS, smem, s>>>(k, tp);
         } else {
-            if (pixel == 0) dog_window45_rot<uint8_t, false><<<grid, CTA_THREADS, smem, s>>>(k, tp);
-            else dog_window45_rot<float, false><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+            if (pixel == 0) dog_window45_rot<uint8_t, 2><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+            else dog_window45_rot<float, 2><<<grid, CTA_THREADS, smem, s>>>(k, tp);
         }
         return cudaGetLastError();
     }
-    if (full) {
-        if (pixel == 0) dog_window45_argmax<uint8_t, true><<<grid, CTA_THREADS, smem, s>>>(k, tp);
-        else dog_window45_argmax<float, true><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+    if (geom == 0) {
+        if (pixel == 0) dog_window45_argmax<uint8_t, 0><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        else dog_window45_argmax<float, 0><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+    } else if (geom == 1) {
+        if (pixel == 0) dog_window45_argmax<uint8_t, 1><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        else dog_window45_argmax<float, 1><<<grid, CTA_THREADS, smem, s>>>(k, tp);
     } else {
-        if (pixel == 0) dog_window45_argmax<uint8_t, false><<<grid, CTA_THREADS, smem, s>>>(k, tp);
-        else dog_window45_argmax<float, false><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        if (pixel == 0) dog_window45_argmax<uint8_t, 2><<<grid, CTA_THREADS, smem, s>>>(k, tp);
+        else dog_window45_argmax<float, 2><<<grid, CTA_THREADS, smem, s>>>(k, tp);
     }
     return cudaGetLastError();
 }
