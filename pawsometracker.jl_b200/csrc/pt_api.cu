@@ -417,7 +417,7 @@ void decompose_cols(pt::WinArgs &a, int nwin, int sms)
 // of the row pass per chunk; two-phase, CTAs are small and uniform (no wave quantisation of one-CTA-per-SM strips).
 bool want_two_phase(const pt_batch *b, const pt::WinArgs &a, int nwin)
 {
-    if (!a.mid || b->cfg.two_phase == 0 || pt::wide_cols_smem_bytes(a.L) + 512 > (size_t)b->cfg.smem_optin) return false;
+    if (!a.mid || b->cfg.two_phase == 0 || pt::wide_cols_smem_bytes(a.L, 1 << 20) + 512 > (size_t)b->cfg.smem_optin) return false;
     // measured (tools/config4_timing.py, tools/tw_sweep.py): faster than the fused kernel for every batch size — one
     // 401x401 window at l = 245: 25 vs 74 µs, 64 of them: 690 vs 725 µs, 256 windows at tw = 70: 225 vs 293 µs
     (void)nwin;

@@ -413,17 +413,25 @@ dog_rows_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
 
 constexpr int PFC = 4;                   // batches of intermediate rows in flight ahead of the column pass
 
-// shared memory of dog_cols_wide: the fused kernel's ring + room for the batches in flight
-__host__ __device__ inline int cols_ring_rows(int L) { return geom64(L).nring + PFC * TB64; }
+// shared memory of dog_cols_wide: the fused kernel's ring + room for the batches in flight — or, when that is more than
+// a chunk's rows altogether (short kernels, low chunks), just those rows: 83 KB instead of 125 KB at l = 77 with 64-row
+// chunks, so two CTAs share an SM and a 256-window launch is one wave instead of two
+__host__ __device__ inline int cols_ring_rows(int L, int CH)
+{
+    const int w = L / 2, pad = (TB64 - (2 * w) % TB64) % TB64;
+    const int all = ((CH + 2 * w + pad + TB64 - 1) / TB64) * TB64;
+    const int ring = geom64(L).nring + PFC * TB64;
+    return all < ring ? all : ring;
+}
 
 template <int DELTA>
-__global__ void __launch_bounds__(THREADS64, 1)
+__global__ void __launch_bounds__(THREADS64, 2)
 dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTaps wt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = a.L, w = a.w;
     Geom64 G = geom64(L);
-    G.nring = cols_ring_rows(L);
+    G.nring = cols_ring_rows(L, a.CH);
     float2 *s_ring = reinterpret_cast<float2 *>(smem_raw);               // [nring][RP64], slot = ring row mod nring
     __shared__ unsigned long long s_best[WARPS64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -470,6 +478,11 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
         }
     };
 
+    // The column pass reads a few ring rows past the support of its outputs (tap counts are padded to multiples of 16,
+    // rows are fetched ahead in runs of 8) and multiplies them by zero taps: whatever the shared memory held before this
+    // CTA must not be NaN or infinity there → the ring starts zeroed, like the fused kernel's.
+    for (int e = tid; e < G.nring * RP64; e += THREADS64) s_ring[e] = make_float2(0.f, 0.f);
+    __syncthreads();
     float best_v = -INFINITY;
     unsigned int best_i = 0xFFFFFFFFu;
     for (int b = 0; b < PFC; ++b) {
@@ -488,7 +501,7 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
 
 int wide_max_kernel_len() { return kMaxLWide; }
 size_t wide_smem_bytes(int L) { return geom64(L).bytes; }
-size_t wide_cols_smem_bytes(int L) { return (size_t)cols_ring_rows(L) * RP64 * sizeof(float2); }
+size_t wide_cols_smem_bytes(int L, int CH) { return (size_t)cols_ring_rows(L, CH) * RP64 * sizeof(float2); }
 // float2 elements of the two-phase intermediate of n windows
 size_t wide_mid_elems(int L, int wr, int wc, int n)
 {
@@ -538,7 +551,7 @@ cudaError_t launch_wide(const WinArgs &a, int n, int pixel, cudaStream_t s)
         // two-phase: every footprint batch row-filtered once, then the column pass per (chunk, strip)
         const Geom64 G = geom64(L);
         const int nbt = (a.wr + 2 * w + TB64 - 1) / TB64;
-        const size_t smem_rows = (size_t)TB64 * G.pin * sizeof(float), smem_cols = wide_cols_smem_bytes(L);
+        const size_t smem_rows = (size_t)TB64 * G.pin * sizeof(float), smem_cols = wide_cols_smem_bytes(L, a.CH);
         dim3 grid_rows((unsigned)(a.strips * nbt * n));
         if (pixel == 0) dog_rows_wide<uint8_t><<<grid_rows, THREADS64, smem_rows, s>>>(a, wt);
         else dog_rows_wide<float><<<grid_rows, THREADS64, smem_rows, s>>>(a, wt);

@@ -124,7 +124,7 @@ cudaError_t launch_generic(const WinArgs &a, int n, int pixel, cudaStream_t s);
 // CTA (l up to ≈ 285), the 32-column kernel above covers longer kernels and narrow windows.
 int wide_max_kernel_len();
 size_t wide_smem_bytes(int L);
-size_t wide_cols_smem_bytes(int L);
+size_t wide_cols_smem_bytes(int L, int CH);
 size_t wide_mid_elems(int L, int wr, int wc, int n);
 cudaError_t wide_init_device();
 cudaError_t launch_wide(const WinArgs &a, int n, int pixel, cudaStream_t s);
