@@ -388,13 +388,13 @@ dog_rows_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
     else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
     const int c0 = strip * SW64, sw = min(SW64, a.wc - c0);
-    for (int e = tid; e < TB64 * G.pin; e += THREADS64) s_in[e] = 0.f;      // incl. the never-used pad columns
+    // (no zero-fill: staging writes every column the row pass consumes, zeros for rows beyond the footprint; the pad
+    // columns left and right are only ever loaded ahead into the register windows, never used)
     const float fill = a.fill[v];
     const PixT *frame = reinterpret_cast<const PixT *>(a.frames) + (size_t)v * a.frame_stride;
     const int X0 = wx0 + c0 - G.w16, Yb = wy0 - w;
     const bool words_ok = sizeof(PixT) == 1 && ((reinterpret_cast<uintptr_t>(frame) | (uintptr_t)a.pitch) & 3u) == 0 &&
                           a.pitch >= ((a.W + 3) & ~3);
-    __syncthreads();
     const int rows_valid = nfoot - b * TB64;
     if (words_ok) stage64_words(reinterpret_cast<const uint8_t *>(frame), a.pitch, a.H, a.W, Yb + b * TB64, X0, rows_valid, fill,
                                 s_in, G.pin, G.nwords, G.width, warp, lane);
