@@ -1124,10 +1124,11 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
     if (b->cfg.zero_copy) {
         pt::WinArgs probe = make_args(b, nullptr, 0, pitch, b->H, b->W, b->d_guess, b->n);
         probe.frame_ptrs = reinterpret_cast<const void *const *>(1);   // "pointer table" marker for the support check
-        bool ok = b->cfg.window45 && pt::window45_supported(probe, b->pixel);
+        const bool w45 = b->cfg.window45 && pt::window45_supported(probe, b->pixel);
+        bool ok = true;
         const size_t frame_bytes = ((size_t)(b->H - 1) * pitch + (size_t)b->W) * px_size(b->pixel);   // first to last byte of a frame
         const size_t cnt = n * (size_t)T;
-        if (ok) { rc = b->h_ptrs.ensure(cnt * sizeof(void *), b); if (rc) return rc; }
+        rc = b->h_ptrs.ensure(cnt * sizeof(void *), b); if (rc) return rc;
         const void **hp = (const void **)b->h_ptrs.p;
         // host address range [rb, rb+rs) already known to be pinned, and its device alias rd
         const char *rb = nullptr, *rd = nullptr; size_t rs = 0;
@@ -1150,9 +1151,9 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
                 }
             }
             hp[i] = rd + (f - rb);
-            if (b->pixel == PT_PIX_U8 && ((uintptr_t)hp[i] & 3u) != 0) { ok = false; break; }
+            if (w45 && b->pixel == PT_PIX_U8 && ((uintptr_t)hp[i] & 3u) != 0) { ok = false; break; }
         }
-        if (ok) {
+        if (ok && w45) {
             rc = b->d_ptrs.ensure(cnt * sizeof(void *), b); if (rc) return rc;
             rc = b->h_traj.ensure(cnt * 20, b); if (rc) return rc;
             int4 *hpos = (int4 *)b->h_traj.p;
@@ -1189,10 +1190,38 @@ int pt_batch_track_host(pt_batch *b, const void *const *frames, int T, size_t pi
             mirror_from_results(b, out_ij + (size_t)(T - 1) * n * 2);
             return PT_OK;
         }
+        // Any other geometry (long kernels, large windows: BASELINE config 4): the streaming kernels read the page-locked
+        // frames in place too — one launch (two for the two-phase wide path) per step, all T steps enqueued at once, the
+        // chain advancing on the device, results stored straight into pinned memory; no crop gather, no per-step copy, no
+        // per-step round trip.  Needs the n frames of a step at one regular stride.
+        if (ok && !w45) {
+            const size_t es = px_size(b->pixel);
+            const ptrdiff_t sv = n > 1 ? (const char *)hp[1] - (const char *)hp[0] : 0;
+            bool regular = sv >= 0 && sv % (ptrdiff_t)es == 0;
+            for (size_t t = 0; regular && t < (size_t)T; ++t)
+                for (size_t v = 0; v < n; ++v)
+                    if ((const char *)hp[t * n + v] != (const char *)hp[t * n] + (ptrdiff_t)v * sv) { regular = false; break; }
+            if (regular) {
+                rc = b->h_traj.ensure(cnt * 20, b); if (rc) return rc;
+                int4 *hpos = (int4 *)b->h_traj.p;
+                float *hresp = (float *)((char *)b->h_traj.p + cnt * 16);
+                rc = flush_guess(b); if (rc) return rc;
+                for (int t = 0; t < T; ++t) {
+                    pt::WinArgs a = make_args(b, hp[(size_t)t * n], (size_t)sv / es, pitch, b->H, b->W, b->d_guess, b->n);
+                    a.host_frames = 1;
+                    a.next_guess = b->d_guess;
+                    a.traj_pos = hpos + (size_t)t * n; a.traj_resp = hresp + (size_t)t * n;
+                    rc = launch_step(b, a, b->n, b->stream); if (rc) return rc;
+                }
+                CU(cudaStreamSynchronize(b->stream));
+                for (size_t i = 0; i < cnt; ++i) { out_ij[2 * i] = hpos[i].x; out_ij[2 * i + 1] = hpos[i].y; if (out_resp) out_resp[i] = hresp[i]; }
+                mirror_from_results(b, out_ij + (size_t)(T - 1) * n * 2);
+                return PT_OK;
+            }
+        }
     }
 
-    // footprint streaming through pinned staging (pageable host frames, or a geometry the chained kernel
-    // does not cover)
+    // footprint streaming through pinned staging (pageable host frames, or pinned frames without a regular layout)
     rc = ensure_lanes(b); if (rc) return rc;
     HostTrack ht;
     ht.b = b; ht.frames = frames; ht.T = T; ht.pitch = pitch; ht.out_ij = out_ij; ht.out_resp = out_resp;

@@ -172,6 +172,16 @@ def test_two_phase_wide_path_in_batches_and_host_lanes(gpu_pkg, oracle, synth, d
             assert b.last_kernel.startswith("dog_rect_argmax_wide" if tp == 0 else "dog_rows_wide"), b.last_kernel
             b.set_guess(start)
             out["host", tp] = b.track_host([[fr[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+        # page-locked frames: read in place by the streaming kernels, all T steps enqueued at once (no crops, no lanes)
+        pin = gpu_pkg.PinnedArray(fr.shape, fr.dtype)
+        pin.array[...] = fr
+        b.set_option("two_phase", 1)
+        b.set_guess(start)
+        lc = b.launch_count
+        out["pinned", 1] = b.track_host([[pin.array[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+        assert b.launch_count - lc == 2 * T, "pinned frames: two launches per step, no per-lane launches"
+        nxt, _ = b.step(None)                                    # the chain state was left on the device
+        pin.close()
     for key, (ij, r) in out.items():
         np.testing.assert_array_equal(ij, out["dev", 0][0], err_msg=str(key))
         np.testing.assert_array_equal(r, out["dev", 0][1], err_msg=str(key))
