@@ -174,7 +174,7 @@ __device__ __forceinline__ void row_pass64(const float *ctr, const WideTaps &wt,
 // Outputs (2p, 2p+1) share a packed accumulator: the ring row met at tap q by output 2p meets tap q−1 at output
 // 2p+1.  Ring rows are numbered n = footprint row − f_first with f_first = o0 − δ a multiple of 8, kept in a
 // 16-slot circular register buffer (slot = n mod 16) and fetched 12 rows ahead in contiguous runs of 8.
-template <int DELTA>
+template <int DELTA, int RP = RP64>
 __device__ __forceinline__ void col_pass64(const WinArgs &a, const WideTaps &wt, const Geom64 &G, const float2 *s_ring, int b,
                                            int w, int ch, int sw, int c0, int r0, int v, int warp, int lane,
                                            float &best_v, unsigned int &best_i, int pad = 0)
@@ -190,24 +190,24 @@ __device__ __forceinline__ void col_pass64(const WinArgs &a, const WideTaps &wt,
         const int f_first = o0 + pad - DELTA;                         // ≡ 0 (mod 8)
         int s0 = f_first % G.nring;
         if (s0 < 0) s0 += G.nring;
-        const float2 *ring_lo = s_ring + col, *ring_hi = s_ring + (size_t)G.nring * RP64 + col;
-        const float2 *run = ring_lo + (size_t)s0 * RP64;              // run of 8 rows holding n = 0 … 7
+        const float2 *ring_lo = s_ring + col, *ring_hi = s_ring + (size_t)G.nring * RP + col;
+        const float2 *run = ring_lo + (size_t)s0 * RP;              // run of 8 rows holding n = 0 … 7
         float2 D[U64];
         float2 accP[R64 / 2], accM[R64 / 2];
 #pragma unroll
         for (int p = 0; p < R64 / 2; ++p) { accP[p] = make_float2(0.f, 0.f); accM[p] = make_float2(0.f, 0.f); }
 #pragma unroll
-        for (int n = 0; n < 8; ++n) D[n] = run[n * RP64];
-        run += 8 * RP64; if (run >= ring_hi) run -= (size_t)G.nring * RP64;
+        for (int n = 0; n < 8; ++n) D[n] = run[n * RP];
+        run += 8 * RP; if (run >= ring_hi) run -= (size_t)G.nring * RP;
 #pragma unroll
-        for (int n = 8; n < 12; ++n) D[n] = run[(n - 8) * RP64];      // run now holds n = 8 … 15
+        for (int n = 8; n < 12; ++n) D[n] = run[(n - 8) * RP];      // run now holds n = 8 … 15
 #pragma unroll 1
         for (int q0 = 0; q0 < G.Lq16; q0 += U64) {
 #pragma unroll
             for (int u = 0; u < U64; ++u) {
                 // fetch row n = q0 + u + 12 (run-relative index (u + 4) mod 8; a new run starts at u = 4 and u = 12)
-                if (u == 4 || u == 12) { run += 8 * RP64; if (run >= ring_hi) run -= (size_t)G.nring * RP64; }
-                D[(u + 12) & 15] = run[((u + 4) & 7) * RP64];
+                if (u == 4 || u == 12) { run += 8 * RP; if (run >= ring_hi) run -= (size_t)G.nring * RP; }
+                D[(u + 12) & 15] = run[((u + 4) & 7) * RP];
                 const float4 gq = wt.cq[q0 + u];                      // warp-uniform index → uniform registers
                 const float2 gp = make_float2(gq.x, gq.y), gm = make_float2(gq.z, gq.w);
 #pragma unroll
@@ -412,6 +412,8 @@ dog_rows_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
 }
 
 constexpr int PFC = 4;                   // batches of intermediate rows in flight ahead of the column pass
+constexpr int RPC = SW64;                // ring row pitch of dog_cols_wide (float2): no row-pass stores here, so no odd pitch —
+                                         // rows are 16-byte aligned (one cp.async per lane and row) and 224 rows fit an SM twice
 
 // shared memory of dog_cols_wide: the fused kernel's ring + room for the batches in flight — or, when that is more than
 // a chunk's rows altogether (short kernels, low chunks), just those rows: 83 KB instead of 125 KB at l = 77 with 64-row
@@ -432,7 +434,7 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     const int L = a.L, w = a.w;
     Geom64 G = geom64(L);
     G.nring = cols_ring_rows(L, a.CH);
-    float2 *s_ring = reinterpret_cast<float2 *>(smem_raw);               // [nring][RP64], slot = ring row mod nring
+    float2 *s_ring = reinterpret_cast<float2 *>(smem_raw);               // [nring][RPC], slot = ring row mod nring
     __shared__ unsigned long long s_best[WARPS64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int v, strip, chunk;
@@ -459,19 +461,18 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     const size_t mp = (size_t)(a.strips * SW64);
     const float2 *mid = a.mid + (size_t)v * nfw * mp + c0;
 
-    // batch b of intermediate rows → ring, asynchronously (cp.async, 8 bytes: ring rows are 8-byte aligned); rows outside
+    // batch b of intermediate rows → ring, asynchronously (cp.async, 16 bytes per lane and row); rows outside
     // the window's footprint are zeros, as the fused kernel stages them
     auto issue_batch = [&](int b) {
 #pragma unroll
         for (int q = 0; q < TB64 / WARPS64; ++q) {
             const int f = b * TB64 + warp + q * WARPS64;
             const int fw = r0 + f - pad;                            // row of the window's footprint
-            float2 *dst = s_ring + (size_t)(f % G.nring) * RP64 + 2 * lane;
+            float2 *dst = s_ring + (size_t)(f % G.nring) * RPC + 2 * lane;
             if (f < nrows && fw >= 0 && fw < nfw) {
                 const float2 *src = mid + (size_t)fw * mp + 2 * lane;
                 const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8u), "l"(src + 1) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
             } else {
                 dst[0] = make_float2(0.f, 0.f); dst[1] = make_float2(0.f, 0.f);
             }
@@ -481,7 +482,7 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     // The column pass reads a few ring rows past the support of its outputs (tap counts are padded to multiples of 16,
     // rows are fetched ahead in runs of 8) and multiplies them by zero taps: whatever the shared memory held before this
     // CTA must not be NaN or infinity there → the ring starts zeroed, like the fused kernel's.
-    for (int e = tid; e < G.nring * RP64; e += THREADS64) s_ring[e] = make_float2(0.f, 0.f);
+    for (int e = tid; e < G.nring * RPC; e += THREADS64) s_ring[e] = make_float2(0.f, 0.f);
     __syncthreads();
     float best_v = -INFINITY;
     unsigned int best_i = 0xFFFFFFFFu;
@@ -494,14 +495,14 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
         __syncthreads();                     // … everybody's; and the column pass of batch b − 1 has finished reading
         if (b + PFC < nb) issue_batch(b + PFC);      // overwrites ring rows older than anything batch b's pass reads
         asm volatile("cp.async.commit_group;" ::: "memory");
-        col_pass64<DELTA>(a, wt, G, s_ring, b, w, ch, sw, c0, r0, v, warp, lane, best_v, best_i, pad);
+        col_pass64<DELTA, RPC>(a, wt, G, s_ring, b, w, ch, sw, c0, r0, v, warp, lane, best_v, best_i, pad);
     }
     merge_and_publish64(a, v, wy0, wx0, best_v, best_i, s_best, tid, warp, lane);
 }
 
 int wide_max_kernel_len() { return kMaxLWide; }
 size_t wide_smem_bytes(int L) { return geom64(L).bytes; }
-size_t wide_cols_smem_bytes(int L, int CH) { return (size_t)cols_ring_rows(L, CH) * RP64 * sizeof(float2); }
+size_t wide_cols_smem_bytes(int L, int CH) { return (size_t)cols_ring_rows(L, CH) * RPC * sizeof(float2); }
 // float2 elements of the two-phase intermediate of n windows
 size_t wide_mid_elems(int L, int wr, int wc, int n)
 {
