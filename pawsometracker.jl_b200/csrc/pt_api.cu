@@ -213,6 +213,8 @@ const pt::Cfg &defaults_from_env()
         cfg.bulk = geti("PT_W45_BULK", 1) ? 1 : 0;
         cfg.wide = geti("PT_GENERIC_WIDE", 1) ? 1 : 0;
         cfg.two_phase = geti("PT_WIDE_TWO_PHASE", 1);
+        cfg.cols_teams = geti("PT_WIDE_COLS_TEAMS", 0);
+        cfg.cols_ch = std::max(0, geti("PT_WIDE_COLS_CH", 0)) / 32 * 32;
     });
     return cfg;
 }
@@ -359,6 +361,7 @@ pt::WinArgs make_args(pt_batch *b, const void *frames, size_t stride, size_t pit
     a.xpos = b->d_xpos;
     a.mid = nullptr;
     a.host_frames = 0;
+    a.cols_teams = b->cfg.cols_teams;
     (void)nwin;
     return a;
 }
@@ -394,7 +397,7 @@ void decompose(pt::WinArgs &a, int nwin, int target)
 // 2w intermediate rows from L2 each; a CTA's cost ≈ copies (≈ 1000 cycles per 32 rows = 16 KB when every SM pulls from L2:
 // 64 windows of 401x401 in 32-row chunks moved 859 MB and took 410 µs) + column pass (32·Lq16 cycles per
 // 32 output rows), CTAs are uniform, so the launch costs whole waves of them.
-void decompose_cols(pt::WinArgs &a, int nwin, int sms)
+void decompose_cols(pt::WinArgs &a, int nwin, int sms, int forced_ch = 0)
 {
     a.strips = (a.wc + 2 * pt::kTileCols - 1) / (2 * pt::kTileCols);
     const int nbo = (a.wr + pt::kBatchRows - 1) / pt::kBatchRows;
@@ -409,6 +412,7 @@ void decompose_cols(pt::WinArgs &a, int nwin, int sms)
         if (cost < best - 1e-9) { best = cost; best_k = k; }
     }
     a.CH = best_k * pt::kBatchRows;
+    if (forced_ch >= pt::kBatchRows) a.CH = std::min(forced_ch / pt::kBatchRows, nbo) * pt::kBatchRows;
     a.chunks = (a.wr + a.CH - 1) / a.CH;
 }
 
@@ -434,7 +438,7 @@ cudaError_t launch_windows(const pt_batch *b, pt::WinArgs &a, int nwin, cudaStre
         return pt::launch_rect45(a, b->cfg, nwin, b->pixel, s);
     a.wide = use_wide_kernel(b, a) ? 1 : 0;
     if (!(a.wide && want_two_phase(b, a, nwin))) a.mid = nullptr;
-    if (a.mid) decompose_cols(a, nwin, b->cfg.sms);
+    if (a.mid) decompose_cols(a, nwin, b->cfg.sms, b->cfg.cols_ch);
     else decompose(a, nwin, b->cfg.generic_target);
     return a.wide ? pt::launch_wide(a, nwin, b->pixel, s) : pt::launch_generic(a, nwin, b->pixel, s);
 }
@@ -1339,7 +1343,7 @@ int pt_batch_set_option(pt_batch *b, const char *name, int value)
         {"mode_slow", &pt::Cfg::mode_slow, 0, 1},     {"zero_copy", &pt::Cfg::zero_copy, 0, 1},
         {"host_lanes", &pt::Cfg::host_lanes, 0, 1024}, {"cluster", &pt::Cfg::cluster, 0, 8},
         {"bulk", &pt::Cfg::bulk, 0, 1},
-        {"wide", &pt::Cfg::wide, 0, 1},               {"two_phase", &pt::Cfg::two_phase, 0, 2},
+        {"wide", &pt::Cfg::wide, 0, 1},               {"two_phase", &pt::Cfg::two_phase, 0, 2},         {"cols_teams", &pt::Cfg::cols_teams, 0, 1},       {"cols_ch", &pt::Cfg::cols_ch, 0, 1 << 16},
     };
     for (const Opt &o : opts) {
         if (strcmp(o.name, name) != 0) continue;

@@ -240,7 +240,7 @@ __device__ __forceinline__ void col_pass64(const WinArgs &a, const WideTaps &wt,
 
 // ---- block argmax → one 64-bit atomicMax per CTA; the last CTA of a window decodes, clamps and publishes
 __device__ __forceinline__ void merge_and_publish64(const WinArgs &a, int v, int wy0, int wx0, float best_v, unsigned int best_i,
-                                                    unsigned long long *s_best, int tid, int warp, int lane)
+                                                    unsigned long long *s_best, int tid, int warp, int lane, int nwarps = WARPS64)
 {
     unsigned long long key = (best_i == 0xFFFFFFFFu) ? 0ull : pack_key(best_v, best_i);
 #pragma unroll
@@ -252,7 +252,7 @@ __device__ __forceinline__ void merge_and_publish64(const WinArgs &a, int v, int
     __syncthreads();
     if (tid == 0) {
         unsigned long long k = s_best[0];
-        for (int i = 1; i < WARPS64; ++i) k = s_best[i] > k ? s_best[i] : k;
+        for (int i = 1; i < nwarps; ++i) k = s_best[i] > k ? s_best[i] : k;
         atomicMax(a.keys + v, k);
         __threadfence();
         const unsigned int total = (unsigned int)(a.strips * a.chunks);
@@ -500,9 +500,94 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     merge_and_publish64(a, v, wy0, wx0, best_v, best_i, s_best, tid, warp, lane);
 }
 
+// dog_cols_wide2: the same with TWO teams of 8 warps per CTA working on two consecutive 32-row output batches at once —
+// for kernels so long that the ring fills an SM (l = 245: one 8-warp CTA per SM, FMA pipe 66 % busy, 12 % of the warp
+// slots).  Intermediate rows arrive in groups of 64; group k + 1 is in flight while the teams run the passes of group k:
+// the ring holds the passes' support (nring rows) + 96.
+__host__ __device__ inline int cols2_ring_rows(int L, int CH)
+{
+    const int w = L / 2, pad = (TB64 - (2 * w) % TB64) % TB64;
+    const int all = ((CH + 2 * w + pad + 2 * TB64 - 1) / (2 * TB64)) * (2 * TB64);
+    const int ring = geom64(L).nring + 3 * TB64;
+    return all < ring ? all : ring;
+}
+
+template <int DELTA>
+__global__ void __launch_bounds__(2 * THREADS64, 1)
+dog_cols_wide2(const __grid_constant__ WinArgs a, const __grid_constant__ WideTaps wt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = a.L, w = a.w;
+    Geom64 G = geom64(L);
+    G.nring = cols2_ring_rows(L, a.CH);
+    float2 *s_ring = reinterpret_cast<float2 *>(smem_raw);               // [nring][RPC], slot = ring row mod nring
+    __shared__ unsigned long long s_best[2 * WARPS64];
+    const int tid = threadIdx.x, lane = tid & 31, warp16 = tid >> 5, team = warp16 >> 3, warp = warp16 & 7;
+    int v, strip, chunk;
+    {
+        const int per_full = a.strips - 1, nc = (int)gridDim.x / a.strips;     // longest-first order, as the fused kernel
+        const int id = (int)blockIdx.x;
+        if (id < per_full * nc) { strip = id % per_full; const int r = id / per_full; chunk = r % a.chunks; v = r / a.chunks; }
+        else { strip = a.strips - 1; const int r = id - per_full * nc; chunk = r % a.chunks; v = r / a.chunks; }
+    }
+    int wy0, wx0;
+    if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
+    else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
+    const int c0 = strip * SW64;
+    const int r0 = chunk * a.CH;
+    const int ch = min(a.CH, a.wr - r0);
+    const int sw = min(SW64, a.wc - c0);
+    const int pad = (TB64 - (2 * w) % TB64) % TB64;        // 2w + pad is a multiple of 32 (see dog_cols_wide)
+    const int nrows = ch + 2 * w + pad;
+    const int nb = (nrows + TB64 - 1) / TB64, ngroups = (nb + 1) / 2;
+    const int nfw = a.wr + 2 * w;
+    const size_t mp = (size_t)(a.strips * SW64);
+    const float2 *mid = a.mid + (size_t)v * nfw * mp + c0;
+
+    auto issue_group = [&](int g) {                         // 64 intermediate rows → ring: 4 rows per warp
+#pragma unroll
+        for (int q = 0; q < 2 * TB64 / (2 * WARPS64); ++q) {
+            const int f = g * 2 * TB64 + warp16 + q * 2 * WARPS64;
+            const int fw = r0 + f - pad;
+            float2 *dst = s_ring + (size_t)(f % G.nring) * RPC + 2 * lane;
+            if (f < nrows && fw >= 0 && fw < nfw) {
+                const float2 *src = mid + (size_t)fw * mp + 2 * lane;
+                const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+            } else {
+                dst[0] = make_float2(0.f, 0.f); dst[1] = make_float2(0.f, 0.f);
+            }
+        }
+    };
+
+    for (int e = tid; e < G.nring * RPC; e += 2 * THREADS64) s_ring[e] = make_float2(0.f, 0.f);   // (see dog_cols_wide)
+    __syncthreads();
+    float best_v = -INFINITY;
+    unsigned int best_i = 0xFFFFFFFFu;
+    // fill-up: nothing is read yet, so every group that fits the ring without wrapping is requested at once
+    int issued = min(G.nring / (2 * TB64), ngroups);
+    for (int g = 0; g < issued; ++g) issue_group(g);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int k = 0; k < ngroups; ++k) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");     // group k has landed (issued ≥ k + 1 here)
+        __syncthreads();                     // … everybody's copies; and the passes of group k − 1 have finished reading
+        if (issued <= k + 1 && issued < ngroups) { issue_group(issued); ++issued; }   // rows older than group k's support
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int b = 2 * k + team;
+        if (b < nb) col_pass64<DELTA, RPC>(a, wt, G, s_ring, b, w, ch, sw, c0, r0, v, warp, lane, best_v, best_i, pad);
+    }
+    merge_and_publish64(a, v, wy0, wx0, best_v, best_i, s_best, tid, warp16, lane, 2 * WARPS64);
+}
+
 int wide_max_kernel_len() { return kMaxLWide; }
 size_t wide_smem_bytes(int L) { return geom64(L).bytes; }
 size_t wide_cols_smem_bytes(int L, int CH) { return (size_t)cols_ring_rows(L, CH) * RPC * sizeof(float2); }
+size_t wide_cols2_smem_bytes(int L, int CH) { return (size_t)cols2_ring_rows(L, CH) * RPC * sizeof(float2); }
+// two teams per CTA where one 8-warp CTA would have the SM to itself anyway and a chunk has at least two output batches
+static bool use_cols2(int L, int CH, size_t smem_limit)
+{
+    return CH >= 2 * TB64 && 2 * (wide_cols_smem_bytes(L, CH) + 1024) > smem_limit && wide_cols2_smem_bytes(L, CH) + 1024 <= smem_limit;
+}
 // float2 elements of the two-phase intermediate of n windows
 size_t wide_mid_elems(int L, int wr, int wc, int n)
 {
@@ -531,6 +616,8 @@ cudaError_t wide_init_device()
     PT_WIDE_OPTIN((dog_rows_wide<float>))
     PT_WIDE_OPTIN((dog_cols_wide<0>))
     PT_WIDE_OPTIN((dog_cols_wide<4>))
+    PT_WIDE_OPTIN((dog_cols_wide2<0>))
+    PT_WIDE_OPTIN((dog_cols_wide2<4>))
 #undef PT_WIDE_OPTIN
     return cudaSuccess;
 }
@@ -558,8 +645,17 @@ cudaError_t launch_wide(const WinArgs &a, int n, int pixel, cudaStream_t s)
         else dog_rows_wide<float><<<grid_rows, THREADS64, smem_rows, s>>>(a, wt);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        if (delta == 0) dog_cols_wide<0><<<grid, THREADS64, smem_cols, s>>>(a, wt);
-        else dog_cols_wide<4><<<grid, THREADS64, smem_cols, s>>>(a, wt);
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (a.cols_teams != 1 && use_cols2(L, a.CH, (size_t)optin)) {
+            const size_t smem2 = wide_cols2_smem_bytes(L, a.CH);
+            if (delta == 0) dog_cols_wide2<0><<<grid, 2 * THREADS64, smem2, s>>>(a, wt);
+            else dog_cols_wide2<4><<<grid, 2 * THREADS64, smem2, s>>>(a, wt);
+        } else {
+            if (delta == 0) dog_cols_wide<0><<<grid, THREADS64, smem_cols, s>>>(a, wt);
+            else dog_cols_wide<4><<<grid, THREADS64, smem_cols, s>>>(a, wt);
+        }
         return cudaGetLastError();
     }
     if (pixel == 0) {

@@ -28,6 +28,8 @@ struct Cfg {
     int host_lanes = 0;       // host threads of the pageable footprint path, 0 = auto  (PT_HOST_LANES)
     int cluster = 0;          // lone-window cluster kernel: 0 auto, 1 off, 2/4/8 CTAs per window (PT_W45_CLUSTER)
     int wide = 1;             // 1: dog_rect_argmax_wide (64-column strips) where it fits, 0: always the 32-column kernel (PT_GENERIC_WIDE)
+    int cols_ch = 0;          // two-phase wide path: output rows per column-kernel chunk (multiple of 32), 0 = cost model (PT_WIDE_COLS_CH)
+    int cols_teams = 0;       // two-phase wide path, column kernel: 0 auto, 1 always one team of 8 warps per CTA (PT_WIDE_COLS_TEAMS)
     int two_phase = 1;        // wide kernel: 0 fused only, 1 auto, 2 always row pass and column pass as two launches (PT_WIDE_TWO_PHASE)
     int smem_optin = 0;       // largest dynamic shared memory per block the device allows (set at create)
     int bulk = 1;             // cluster kernel staging: 1 = one TMA tile copy per step into shared memory, 0 = global loads (PT_W45_BULK)
@@ -70,6 +72,7 @@ struct WinArgs {
     int2 *xpos;                // [n] hand-off guesses } the kernel leaves them zeroed
     const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
     int host_frames;           // frames/strides address page-locked HOST memory (zero-copy over PCIe): changes the cluster policy only
+    int cols_teams;            // dog_cols_wide: 0 auto, 1 one team of 8 warps per CTA always (option "cols_teams")
     float2 *mid;               // two-phase wide path: row-pass intermediate [n][wr + 2w][strips·64] (null = fused kernel)
 };
 

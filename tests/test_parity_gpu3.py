@@ -191,3 +191,37 @@ def test_two_phase_wide_path_in_batches_and_host_lanes(gpu_pkg, oracle, synth, d
         if near == 0:
             np.testing.assert_array_equal(ij0[:, v], pos)
         assert np.all(np.abs(r0[:, v] - resp) <= np.maximum(RTOL * mx, BLANK))
+
+
+@pytest.mark.parametrize("tw,ws", [(100, (150, 70)), (70, (121, 121))])
+def test_two_team_column_kernel(gpu_pkg, oracle, tw, ws):
+    """dog_cols_wide2 (two teams of 8 warps per CTA on two consecutive output batches, for kernels whose ring fills an SM)
+    against the one-team kernel for several chunk heights: bit-identical response maps and results; map vs the oracle."""
+    darker = False
+    l = oracle.kernel_len(tw)
+    rng = np.random.default_rng(int(tw))
+    H, W = ws[0] + 40, ws[1] + 64
+    f8 = rng.integers(90, 170, (H, W)).astype(np.uint8)
+    yy, xx = np.ogrid[0:H, 0:W]
+    f8[(yy - H // 2 - 5) ** 2 + (xx - W // 2 + 7) ** 2 <= (int(tw) // 2) ** 2] = 250
+    guess = (H // 2, W // 2)
+    fill = oracle.mode(f8)
+    ref = oracle.step(f8, fill, tw, darker, ws, guess, dense=False, want_map=True)
+    maps, outs = {}, {}
+    for ch in (0, 64, 96, 160):
+        for teams in (0, 1):
+            trk = gpu_pkg.Tracker(f8, tw, ws, darker)
+            try:
+                trk.set_option("two_phase", 2); trk.set_option("cols_ch", ch); trk.set_option("cols_teams", teams)
+                outs[ch, teams] = (trk.step_resident(guess), trk.last_response)
+                maps[ch, teams] = trk.response_map(guess)
+                assert trk._batch.last_kernel.startswith("dog_rows_wide")
+            finally:
+                trk.close()
+    base = maps[0, 1]
+    assert np.abs(base.astype(np.float64) - ref.R).max() <= RTOL * ref.maxabs
+    for k, m in maps.items():
+        np.testing.assert_array_equal(m, base, err_msg=str(k))
+        assert outs[k] == outs[0, 1], k
+    if not ref.near_tie(RTOL):
+        assert outs[0, 1][0] == (ref.i, ref.j)
