@@ -380,6 +380,9 @@ dog_rows_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     const int L = a.L, w = a.w;
     const Geom64 G = geom64(L);
     float *s_in = reinterpret_cast<float *>(smem_raw);                    // [32][pin]
+    // programmatic dependent launch: the column kernel may be scheduled as soon as every CTA of this grid is running (it
+    // zeroes its ring meanwhile and waits for this grid's completion — griddepcontrol.wait — before it reads the intermediate)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nfoot = a.wr + 2 * w, nbt = (nfoot + TB64 - 1) / TB64;
     const int id = (int)blockIdx.x;
@@ -483,6 +486,7 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     // rows are fetched ahead in runs of 8) and multiplies them by zero taps: whatever the shared memory held before this
     // CTA must not be NaN or infinity there → the ring starts zeroed, like the fused kernel's.
     for (int e = tid; e < G.nring * RPC; e += THREADS64) s_ring[e] = make_float2(0.f, 0.f);
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // the row kernel's intermediate is complete and visible
     __syncthreads();
     float best_v = -INFINITY;
     unsigned int best_i = 0xFFFFFFFFu;
@@ -561,6 +565,7 @@ dog_cols_wide2(const __grid_constant__ WinArgs a, const __grid_constant__ WideTa
     };
 
     for (int e = tid; e < G.nring * RPC; e += 2 * THREADS64) s_ring[e] = make_float2(0.f, 0.f);   // (see dog_cols_wide)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     float best_v = -INFINITY;
     unsigned int best_i = 0xFFFFFFFFu;
@@ -648,15 +653,18 @@ cudaError_t launch_wide(const WinArgs &a, int n, int pixel, cudaStream_t s)
         int dev = 0, optin = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = grid; lc.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
         if (a.cols_teams != 1 && use_cols2(L, a.CH, (size_t)optin)) {
-            const size_t smem2 = wide_cols2_smem_bytes(L, a.CH);
-            if (delta == 0) dog_cols_wide2<0><<<grid, 2 * THREADS64, smem2, s>>>(a, wt);
-            else dog_cols_wide2<4><<<grid, 2 * THREADS64, smem2, s>>>(a, wt);
-        } else {
-            if (delta == 0) dog_cols_wide<0><<<grid, THREADS64, smem_cols, s>>>(a, wt);
-            else dog_cols_wide<4><<<grid, THREADS64, smem_cols, s>>>(a, wt);
+            lc.blockDim = dim3(2 * THREADS64); lc.dynamicSmemBytes = wide_cols2_smem_bytes(L, a.CH);
+            return delta == 0 ? cudaLaunchKernelEx(&lc, dog_cols_wide2<0>, a, wt) : cudaLaunchKernelEx(&lc, dog_cols_wide2<4>, a, wt);
         }
-        return cudaGetLastError();
+        lc.blockDim = dim3(THREADS64); lc.dynamicSmemBytes = smem_cols;
+        return delta == 0 ? cudaLaunchKernelEx(&lc, dog_cols_wide<0>, a, wt) : cudaLaunchKernelEx(&lc, dog_cols_wide<4>, a, wt);
     }
     if (pixel == 0) {
         if (delta == 0) dog_rect_argmax_wide<uint8_t, 0><<<grid, THREADS64, smem, s>>>(a, wt);
