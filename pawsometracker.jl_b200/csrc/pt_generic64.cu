@@ -383,6 +383,9 @@ dog_rows_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     // programmatic dependent launch: the column kernel may be scheduled as soon as every CTA of this grid is running (it
     // zeroes its ring meanwhile and waits for this grid's completion — griddepcontrol.wait — before it reads the intermediate)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // … and this kernel is itself a dependent launch of whatever precedes it in the stream (in a chain of steps: the
+    // previous step's column kernel, which wrote the guess read below): its launch latency overlaps that kernel's tail
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nfoot = a.wr + 2 * w, nbt = (nfoot + TB64 - 1) / TB64;
     const int id = (int)blockIdx.x;
@@ -439,6 +442,7 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     G.nring = cols_ring_rows(L, a.CH);
     float2 *s_ring = reinterpret_cast<float2 *>(smem_raw);               // [nring][RPC], slot = ring row mod nring
     __shared__ unsigned long long s_best[WARPS64];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // (the next step's row kernel may be scheduled)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int v, strip, chunk;
     {
@@ -447,9 +451,6 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
         if (id < per_full * nc) { strip = id % per_full; const int r = id / per_full; chunk = r % a.chunks; v = r / a.chunks; }
         else { strip = a.strips - 1; const int r = id - per_full * nc; chunk = r % a.chunks; v = r / a.chunks; }
     }
-    int wy0, wx0;
-    if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
-    else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
     const int c0 = strip * SW64;
     const int r0 = chunk * a.CH;
     const int ch = min(a.CH, a.wr - r0);
@@ -486,7 +487,13 @@ dog_cols_wide(const __grid_constant__ WinArgs a, const __grid_constant__ WideTap
     // rows are fetched ahead in runs of 8) and multiplies them by zero taps: whatever the shared memory held before this
     // CTA must not be NaN or infinity there → the ring starts zeroed, like the fused kernel's.
     for (int e = tid; e < G.nring * RPC; e += THREADS64) s_ring[e] = make_float2(0.f, 0.f);
-    asm volatile("griddepcontrol.wait;" ::: "memory");       // the row kernel's intermediate is complete and visible
+    // Everything above touched nothing an earlier kernel writes.  From here on: the row kernel's intermediate — and, since
+    // the kernels of a chain of steps run ahead of one another up to this point, the guess the PREVIOUS step's column
+    // kernel published — are complete and visible.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    int wy0, wx0;
+    if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
+    else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
     __syncthreads();
     float best_v = -INFINITY;
     unsigned int best_i = 0xFFFFFFFFu;
@@ -526,6 +533,7 @@ dog_cols_wide2(const __grid_constant__ WinArgs a, const __grid_constant__ WideTa
     G.nring = cols2_ring_rows(L, a.CH);
     float2 *s_ring = reinterpret_cast<float2 *>(smem_raw);               // [nring][RPC], slot = ring row mod nring
     __shared__ unsigned long long s_best[2 * WARPS64];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31, warp16 = tid >> 5, team = warp16 >> 3, warp = warp16 & 7;
     int v, strip, chunk;
     {
@@ -534,9 +542,6 @@ dog_cols_wide2(const __grid_constant__ WinArgs a, const __grid_constant__ WideTa
         if (id < per_full * nc) { strip = id % per_full; const int r = id / per_full; chunk = r % a.chunks; v = r / a.chunks; }
         else { strip = a.strips - 1; const int r = id - per_full * nc; chunk = r % a.chunks; v = r / a.chunks; }
     }
-    int wy0, wx0;
-    if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
-    else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
     const int c0 = strip * SW64;
     const int r0 = chunk * a.CH;
     const int ch = min(a.CH, a.wr - r0);
@@ -565,7 +570,10 @@ dog_cols_wide2(const __grid_constant__ WinArgs a, const __grid_constant__ WideTa
     };
 
     for (int e = tid; e < G.nring * RPC; e += 2 * THREADS64) s_ring[e] = make_float2(0.f, 0.f);   // (see dog_cols_wide)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // (see dog_cols_wide: nothing written by an earlier kernel is read above)
+    int wy0, wx0;
+    if (a.rect_mode) { wy0 = a.ry0; wx0 = a.rx0; }
+    else { const int2 g = a.guess[v]; wy0 = g.x - 1 - a.rr; wx0 = g.y - 1 - a.rc; }
     __syncthreads();
     float best_v = -INFINITY;
     unsigned int best_i = 0xFFFFFFFFu;
@@ -646,9 +654,13 @@ cudaError_t launch_wide(const WinArgs &a, int n, int pixel, cudaStream_t s)
         const int nbt = (a.wr + 2 * w + TB64 - 1) / TB64;
         const size_t smem_rows = (size_t)TB64 * G.pin * sizeof(float), smem_cols = wide_cols_smem_bytes(L, a.CH);
         dim3 grid_rows((unsigned)(a.strips * nbt * n));
-        if (pixel == 0) dog_rows_wide<uint8_t><<<grid_rows, THREADS64, smem_rows, s>>>(a, wt);
-        else dog_rows_wide<float><<<grid_rows, THREADS64, smem_rows, s>>>(a, wt);
-        cudaError_t e = cudaGetLastError();
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t lr = {};
+        lr.gridDim = grid_rows; lr.blockDim = dim3(THREADS64); lr.dynamicSmemBytes = smem_rows; lr.stream = s;
+        lr.attrs = pdl; lr.numAttrs = 1;
+        cudaError_t e = pixel == 0 ? cudaLaunchKernelEx(&lr, dog_rows_wide<uint8_t>, a, wt) : cudaLaunchKernelEx(&lr, dog_rows_wide<float>, a, wt);
         if (e != cudaSuccess) return e;
         int dev = 0, optin = 0;
         cudaGetDevice(&dev);

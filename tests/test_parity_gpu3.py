@@ -225,3 +225,36 @@ def test_two_team_column_kernel(gpu_pkg, oracle, tw, ws):
         assert outs[k] == outs[0, 1], k
     if not ref.near_tie(RTOL):
         assert outs[0, 1][0] == (ref.i, ref.j)
+
+
+def test_two_phase_chain_runs_ahead_safely(gpu_pkg, synth):
+    """The row and column kernels of consecutive steps are programmatic dependent launches of one another: a kernel may
+    start before its predecessor has finished and must read nothing the predecessor writes (the published guess above
+    all) before its griddepcontrol.wait.  A long chain over page-locked host frames — slow row kernels, the widest window
+    for a kernel to run ahead in — must equal the chain over resident frames and the step-by-step calls."""
+    import torch
+    tw, ws, darker = 55, (97, 97), True
+    n, T, H, W = 6, 14, 178, 88
+    frames, start = make_case(synth, H, W, n, T, tw, darker, 1234)
+    dev = torch.from_numpy(frames).cuda()
+    pin = gpu_pkg.PinnedArray(frames.shape, frames.dtype)
+    pin.array[...] = frames
+    with gpu_pkg.TrackerBatch(n, (H, W), tw, ws, darker) as b:
+        b.bind_device_frames(dev.data_ptr(), H * W, W)
+        b.compute_fill()
+        b.set_guess(start)
+        ij_res, r_res = b.track_device(dev.data_ptr(), n * H * W, H * W, W, T)
+        assert b.last_kernel.startswith("dog_rows_wide")
+        for rep in range(3):
+            b.set_guess(start)
+            ij_pin, r_pin = b.track_host([[pin.array[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+            np.testing.assert_array_equal(ij_pin, ij_res)
+            np.testing.assert_array_equal(r_pin, r_res)
+        b.set_guess(start)
+        per_step = []
+        for t in range(T):
+            b.bind_device_frames(dev.data_ptr() + t * n * H * W, H * W, W)
+            o, rr = b.step(None)
+            per_step.append(o.copy())
+        np.testing.assert_array_equal(np.stack(per_step), ij_res)
+    pin.close()
