@@ -56,6 +56,14 @@ class ArrayVideo:
         f = self.frames[k]
         return f if isinstance(f, np.ndarray) and f.ndim == 2 and f.strides[1] == f.itemsize else None
 
+    def frame_addresses(self, idx: np.ndarray):
+        """Addresses of the frames `idx` (an int64 array) as one int64 array + (shape, dtype, row pitch in elements), when
+        the video is ONE (T, H, W) array with contiguous rows — no per-frame Python objects; else None."""
+        a = self.frames
+        if not (isinstance(a, np.ndarray) and a.ndim == 3 and a.strides[2] == a.itemsize and a.strides[1] % a.itemsize == 0):
+            return None
+        return a.ctypes.data + idx * a.strides[0], a.shape[1:], a.dtype, a.strides[1] // a.itemsize
+
 
 class CvVideo:
     """A real video file decoded on the host with OpenCV's FFmpeg backend to
@@ -131,6 +139,23 @@ class _Resampled:
         f = self.vid.frame(self._src_index(self.k), out)
         self.k += 1
         return f
+
+    def read_ref_block(self, kmax: int):
+        """The next ≤ kmax frames by ADDRESS in one vectorised step (sources that hold all frames in one array): returns
+        (int64 address array, shape, dtype, pitch) and advances, or None when the source cannot do that."""
+        get = getattr(self.vid, "frame_addresses", None)
+        if get is None or self.k >= self.limit:
+            return None
+        k = np.arange(self.k, min(self.limit, self.k + int(kmax)), dtype=np.float64)
+        idx = np.floor((self.start + k / self.fps) * self.vid.fps + 0.5).astype(np.int64)     # _src_index, vectorised
+        idx = idx[idx < len(self.vid)]
+        if idx.size == 0:
+            return None
+        r = get(idx)
+        if r is None:
+            return None
+        self.k += int(idx.size)
+        return r
 
     def read_ref(self):
         """Next frame by reference when the source can give one (no copy into the tracker's buffer), else None
@@ -248,6 +273,7 @@ def get_start_ij_and_tracker(start_location, vid, img, target_width, window_size
 
 CHUNK_FRAMES = 64        # frames per chained library call of track_one (the depth of the page-locked decode ring)
 CHUNK_FRAMES_REF = 256   # … when the source hands its frames out by reference (no ring to allocate)
+CHUNK_FRAMES_BLOCK = 1024  # … when it hands out whole blocks of frame addresses (frames in one array)
 
 
 def _track_chunks(trckr, vid, n, indices):
@@ -261,6 +287,16 @@ def _track_chunks(trckr, vid, n, indices):
     H, W = trckr.sz
     dtype = trckr.img.dtype
     contiguous = (W * dtype.itemsize, dtype.itemsize)
+    # sources that hold every frame in one array: whole chunks by address, no per-frame Python work
+    while len(indices) < n and not vid.eof():
+        blk = vid.read_ref_block(min(CHUNK_FRAMES_BLOCK, n - len(indices))) if hasattr(vid, "read_ref_block") else None
+        if blk is None:
+            break
+        addrs, shape, dt, pitch = blk
+        if tuple(shape) != (H, W) or dt != dtype:
+            raise ValueError(f"DimensionMismatch: frames are {tuple(shape)} {dt}, tracker was built for {(H, W)} {dtype}")
+        ij, _ = trckr.track_addresses(addrs, pitch, indices[-1])
+        indices.extend(map(tuple, ij.tolist()))
     try:
         pending = None                       # a consumed frame that needs a ring slot of the NEXT chunk
         while (pending is not None or not vid.eof()) and len(indices) < n:

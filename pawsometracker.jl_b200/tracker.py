@@ -325,6 +325,21 @@ class Tracker:
         self.last_response = float(resp[-1])
         return out, resp
 
+    def track_addresses(self, addrs: np.ndarray, pitch: int, guess):
+        """track_frames for frames given by ADDRESS (an int64 array, one host frame each, rows `pitch` elements apart):
+        the caller vouches for shape and dtype.  One library call for the whole block."""
+        addrs = np.ascontiguousarray(addrs, np.int64)
+        T = int(addrs.size)
+        g = (C.c_int32 * 2)(int(guess[0]), int(guess[1]))
+        out = np.empty((T, 2), np.int32)
+        resp = np.empty(T, np.float32)
+        h = self._batch._h
+        check(lib.pt_batch_set_guess(h, g))
+        check(lib.pt_batch_track_host(h, addrs.ctypes.data_as(C.POINTER(C.c_void_p)), T, int(pitch), 0,
+                                      out.ctypes.data_as(_i32p), resp.ctypes.data_as(_fp)))
+        self.last_response = float(resp[-1])
+        return out, resp
+
     def step_resident(self, guess):
         """Same result with the whole frame uploaded to HBM first (the
         `read!` + step of the reference's loop, :166-167)."""

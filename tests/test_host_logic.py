@@ -143,3 +143,31 @@ def test_track_chunks_frame_order_for_every_kind_of_source(pkg, monkeypatch):
             ind = [(0, 0)]
             api._track_chunks(FakeTrk(), Src(n, by_ref), min(n, 40) + 1, ind)      # stop before the source ends
             assert [a for a, _ in ind[1:]] == [k % 251 for k in range(min(n, 40))]
+
+
+def test_resampler_block_addresses_equal_per_frame_reads(pkg):
+    """_Resampled.read_ref_block (vectorised frame selection + addresses for sources that hold all frames in one array)
+    picks exactly the frames the per-frame path picks (`ffmpeg -ss start -t t -vf fps=fps`, src/PawsomeTracker.jl:155)."""
+    import sys
+    api = sys.modules[pkg.__name__ + ".api"]
+    rng = np.random.default_rng(5)
+    arr = rng.integers(0, 256, (97, 6, 8)).astype(np.uint8)
+    for start, t, fps, src_fps in [(0.0, 4.0, 24.0, 24.0), (0.25, 3.0, 12.0, 24.0), (1.0, 10.0, 30.0, 24.0), (0.1, 2.5, 7.5, 25.0)]:
+        a = api._Resampled(api.ArrayVideo(arr, fps=src_fps), start, t, fps)
+        b = api._Resampled(api.ArrayVideo(arr, fps=src_fps), start, t, fps)
+        per_frame = []
+        while not a.eof():
+            per_frame.append(a.read_ref())
+        got = []
+        while True:
+            blk = b.read_ref_block(5)
+            if blk is None:
+                break
+            addrs, shape, dt, pitch = blk
+            assert tuple(shape) == (6, 8) and dt == np.uint8 and pitch == 8
+            got.extend(int(x) for x in addrs)
+        assert b.eof()
+        assert got == [f.ctypes.data for f in per_frame]
+    # a list of frames cannot be addressed as a block
+    c = api._Resampled(api.ArrayVideo([arr[0], arr[1]], fps=24.0), 0.0, 1.0, 24.0)
+    assert c.read_ref_block(4) is None and not c.eof()

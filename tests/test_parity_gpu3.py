@@ -258,3 +258,32 @@ def test_two_phase_chain_runs_ahead_safely(gpu_pkg, synth):
             per_step.append(o.copy())
         np.testing.assert_array_equal(np.stack(per_step), ij_res)
     pin.close()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_track_over_one_array_of_frames(gpu_pkg, oracle, synth, pinned):
+    """track() on a video held as ONE (T, H, W) array (pageable or page-locked): whole blocks of frame addresses go to the
+    library in one call each; with start > 0 and fps resampling the positions equal the oracle loop on the selected frames."""
+    tw = 25
+    vid = synth.make_video(H=200, W=256, target_width=tw, start_ij=(100, 128), seconds=6.0, fps=24.0, seed=9)
+    frames = np.stack([vid.frame(k) for k in range(144)])
+    pin = None
+    if pinned:
+        pin = gpu_pkg.PinnedArray(frames.shape, np.uint8)
+        pin.array[...] = frames
+    src = pin.array if pinned else frames
+    start, stop, fps = 0.5, 5.5, 12.0
+    ts, ij = gpu_pkg.track(gpu_pkg.ArrayVideo(src, fps=24.0), start=start, stop=stop, target_width=tw,
+                           start_location=gpu_pkg.CartesianIndex(*[int(x) for x in vid.traj[12]]), darker_target=True, fps=fps)
+    n = int(round(fps * (stop - start)))
+    sel = [int(np.floor((start + k / fps) * 24.0 + 0.5)) for k in range(n)]
+    sel = [k for k in sel if k < len(frames)]
+    assert len(ij) == len(sel)
+    fill = oracle.mode(frames[sel[0]])
+    g = tuple(int(x) for x in vid.traj[12])
+    for k, fi in enumerate(sel):
+        r = oracle.step(frames[fi], fill, tw, True, (45, 45), g, dense=True)
+        assert tuple(ij[k]) == (r.i, r.j), k
+        g = (r.i, r.j)
+    if pin is not None:
+        pin.close()
