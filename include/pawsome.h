@@ -178,7 +178,7 @@ PT_API int pt_batch_read_track(pt_batch *b, int T, int32_t *out_ij, float *out_r
  * come from PT_* environment variables read once at the first pt_batch_create.  Names: "window45" (0: force the
  * generic kernel), "rect45", "rot" (0 off / 1 auto / 2 always / 3 always, handshake forced to the static schedule), "rot_stride" (slots the empty arc of the rotating schedule advances per step, 0 = its own length), "skew", "r45_chunks" (0 = cost model),
  * "generic_target", "mode_slow", "zero_copy", "host_lanes", "cluster" (0 auto / 1 off / 2, 4, 8 CTAs per lone
- * window), "bulk" (1: TMA staging of the cluster kernel, 0: global loads), "wide" (0: 32-column generic kernel only), "two_phase" (64-column kernel: 0 fused, 1 auto, 2 always row pass and column pass as two launches), "cols_teams" (column kernel of the two-phase path: 0 auto, 1 never two teams per CTA), "cols_ch" (its rows per chunk, 0 = cost model).  Unknown name or value out of range: PT_ERR_ARG. */
+ * window), "bulk" (1: TMA staging of the cluster kernel, 0: global loads), "wide" (0: 32-column generic kernel only), "two_phase" (64-column kernel: 0 fused, 1 auto, 2 always row pass and column pass as two launches), "cols_teams" (column kernel of the two-phase path: 0 auto, 1 never two teams per CTA), "cols_ch" (its rows per chunk, 0 = cost model), "crop_gather" (page-locked host frames outside the per-window kernels: 1 footprints copied to device crops once per step, 0 read in place).  Unknown name or value out of range: PT_ERR_ARG. */
 PT_API int pt_batch_set_option(pt_batch *b, const char *name, int value);
 
 /* Introspection for the harness: kernels launched by this handle so far, and

@@ -670,4 +670,65 @@ cudaError_t launch_downscale(const void *frames, size_t frame_stride, int pitch,
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// gather_footprints — for page-locked HOST frames and geometries the chained per-window kernels do not cover (long
+// kernels, large windows): copy each window's footprint out of its host frame into a device crop, ONCE per step and in
+// 16-byte pieces (the streaming kernels would re-read the kernel-length halos of their column strips over PCIe: 1.4 MB
+// instead of 0.4 MB per 401x401 window at l = 245).  The window position is on the device (the chain advances there), so
+// the copy is a kernel, not a DMA descriptor.  Crop column 0 is the frame column ox = (footprint origin) rounded down to a
+// 16-byte boundary; everything outside the frame is the fill value (the PaddedView border, src/PawsomeTracker.jl:48), so the
+// filter kernels see a frame of fr x cp pixels that contains the whole footprint.  Also written: the crop's origin in
+// the frame (publish_result translates the argmax back and clamps to the REAL frame, :60-61) and the guess in crop
+// coordinates.
+// ---------------------------------------------------------------------------------------------------
+template <typename PixT>
+__global__ void __launch_bounds__(256)
+gather_footprints(const void *frames, size_t frame_stride, int pitch, int H, int W, const int2 *guess, const float *fill,
+                  int rr, int rc, int w, int fr, int cp, void *crops, size_t crop_stride, int2 *org, int2 *cguess)
+{
+    constexpr int EPC = 16 / (int)sizeof(PixT);              // elements per 16-byte piece
+    const int v = blockIdx.y;
+    const int2 g = guess[v];
+    const int oy = g.x - 1 - rr - w;
+    const int ox = (g.y - 1 - rc - w) & ~(EPC - 1);          // rounds down (two's complement), also when negative
+    if (blockIdx.x == 0 && threadIdx.x == 0) { org[v] = make_int2(oy, ox); cguess[v] = make_int2(g.x - oy, g.y - ox); }
+    const int nc = cp / EPC;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= fr * nc) return;
+    const int y = e / nc, c = e - y * nc;
+    const int Y = oy + y, X0 = ox + c * EPC;
+    const PixT *frame = reinterpret_cast<const PixT *>(frames) + (size_t)v * frame_stride;
+    PixT *dst = reinterpret_cast<PixT *>(crops) + (size_t)v * crop_stride + (size_t)y * cp + c * EPC;
+    PixT fv;
+    if (sizeof(PixT) == 1) fv = (PixT)(unsigned char)fill[v]; else fv = (PixT)fill[v];
+    const bool yok = Y >= 0 && Y < H;
+    const PixT *src = frame + (size_t)(yok ? Y : 0) * pitch + X0;
+    if (yok && X0 >= 0 && X0 + EPC <= W && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        uint4 q;
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(src));
+        *reinterpret_cast<uint4 *>(dst) = q;
+    } else {
+        PixT tmp[EPC];
+#pragma unroll
+        for (int k = 0; k < EPC; ++k) {
+            const int X = X0 + k;
+            tmp[k] = (yok && X >= 0 && X < W) ? src[k] : fv;
+        }
+#pragma unroll
+        for (int k = 0; k < EPC; ++k) dst[k] = tmp[k];
+    }
+}
+
+cudaError_t launch_gather_footprints(const void *frames, size_t frame_stride, int pitch, int H, int W, int n, int pixel,
+                                     const int2 *guess, const float *fill, int rr, int rc, int w, int fr, int cp,
+                                     void *crops, size_t crop_stride, int2 *org, int2 *cguess, cudaStream_t s)
+{
+    const int epc = pixel == 0 ? 16 : 4;
+    const long long pieces = (long long)fr * (cp / epc);
+    dim3 grid((unsigned)((pieces + 255) / 256), (unsigned)n);
+    if (pixel == 0) gather_footprints<uint8_t><<<grid, 256, 0, s>>>(frames, frame_stride, pitch, H, W, guess, fill, rr, rc, w, fr, cp, crops, crop_stride, org, cguess);
+    else gather_footprints<float><<<grid, 256, 0, s>>>(frames, frame_stride, pitch, H, W, guess, fill, rr, rc, w, fr, cp, crops, crop_stride, org, cguess);
+    return cudaGetLastError();
+}
+
 } // namespace pt

@@ -28,6 +28,7 @@ struct Cfg {
     int host_lanes = 0;       // host threads of the pageable footprint path, 0 = auto  (PT_HOST_LANES)
     int cluster = 0;          // lone-window cluster kernel: 0 auto, 1 off, 2/4/8 CTAs per window (PT_W45_CLUSTER)
     int wide = 1;             // 1: dog_rect_argmax_wide (64-column strips) where it fits, 0: always the 32-column kernel (PT_GENERIC_WIDE)
+    int crop_gather = 1;      // page-locked host frames, geometries outside the per-window kernels: 1 = copy each footprint into a device crop once per step (gather_footprints), 0 = the filter kernels read the host frames in place (PT_CROP_GATHER)
     int cols_ch = 0;          // two-phase wide path: output rows per column-kernel chunk (multiple of 32), 0 = cost model (PT_WIDE_COLS_CH)
     int cols_teams = 0;       // two-phase wide path, column kernel: 0 auto, 1 always one team of 8 warps per CTA (PT_WIDE_COLS_TEAMS)
     int two_phase = 1;        // wide kernel: 0 fused only, 1 auto, 2 always row pass and column pass as two launches (PT_WIDE_TWO_PHASE)
@@ -73,6 +74,8 @@ struct WinArgs {
     const float *h_taps;       // HOST copy of the taps: [L] row narrow, [L] row wide, [L] col narrow, [L] col wide
     int host_frames;           // frames/strides address page-locked HOST memory (zero-copy over PCIe): changes the cluster policy only
     int cols_teams;            // dog_cols_wide: 0 auto, 1 one team of 8 warps per CTA always (option "cols_teams")
+    const int2 *crop_org;      // frames are per-window crops (gather_footprints): origin (row, col) of each crop in its real frame, else null
+    int Hreal, Wreal;          // … and the real frame size results are clamped to
     float2 *mid;               // two-phase wide path: row-pass intermediate [n][wr + 2w][strips·64] (null = fused kernel)
 };
 
@@ -106,7 +109,9 @@ __device__ __forceinline__ void publish_result(const WinArgs &a, int v, unsigned
     int xx = (int)(idx / (unsigned int)a.wr);
     int yy = (int)(idx - (unsigned int)xx * (unsigned int)a.wr);
     int raw_i = wy0 + yy + 1, raw_j = wx0 + xx + 1;
-    int ci = min(max(raw_i, 1), a.H), cj = min(max(raw_j, 1), a.W);
+    int Hc = a.H, Wc = a.W;
+    if (a.crop_org) { const int2 o = a.crop_org[v]; raw_i += o.x; raw_j += o.y; Hc = a.Hreal; Wc = a.Wreal; }   // crop → frame
+    int ci = min(max(raw_i, 1), Hc), cj = min(max(raw_j, 1), Wc);
     float resp = key_value(key);
     int4 p = make_int4(ci, cj, raw_i, raw_j);
     a.out_pos[v] = p;
@@ -153,6 +158,11 @@ constexpr int kModeScratch = 832;
 cudaError_t launch_mode(const void *frames, size_t frame_stride, int pitch, int H, int W, int n,
                         int pixel, unsigned int *hist, float *fill_out, int *fill_int_out,
                         bool force_slow, cudaStream_t s);
+
+// Footprints of page-locked host frames → device crops, once per step (see gather_footprints in pt_kernels.cu).
+cudaError_t launch_gather_footprints(const void *frames, size_t frame_stride, int pitch, int H, int W, int n, int pixel,
+                                     const int2 *guess, const float *fill, int rr, int rc, int w, int fr, int cp,
+                                     void *crops, size_t crop_stride, int2 *org, int2 *cguess, cudaStream_t s);
 
 // imresize!(dia.buffer, img) (src/diagnose.jl:33): current frame of n videos → [n][oh][ow] u8, bilinear, centre-aligned.
 cudaError_t launch_downscale(const void *frames, size_t frame_stride, int pitch, int H, int W, int n, int pixel,

@@ -179,7 +179,11 @@ def test_two_phase_wide_path_in_batches_and_host_lanes(gpu_pkg, oracle, synth, d
         b.set_guess(start)
         lc = b.launch_count
         out["pinned", 1] = b.track_host([[pin.array[t, v] for v in range(n)] for t in range(T)], mode="footprint")
-        assert b.launch_count - lc == 2 * T, "pinned frames: two launches per step, no per-lane launches"
+        assert b.launch_count - lc == 3 * T, "pinned frames: footprint gather + two filter launches per step, no per-lane launches"
+        b.set_option("crop_gather", 0)                           # the same with the filter kernels reading the host frames in place
+        b.set_guess(start)
+        out["pinned in place", 1] = b.track_host([[pin.array[t, v] for v in range(n)] for t in range(T)], mode="footprint")
+        b.set_option("crop_gather", 1)
         nxt, _ = b.step(None)                                    # the chain state was left on the device
         pin.close()
     for key, (ij, r) in out.items():
