@@ -263,8 +263,9 @@ def get_start_ij_and_tracker(start_location, vid, img, target_width, window_size
         window_size2 = (sz[0] // 4, sz[1] // 4)                 # "this greatly affects processing time!" (:102)
         trckr = Tracker(img, target_width, window_size2, darker_target, device)   # auto-detection pass (:103)
         ij = trckr(guess)
+        fill = trckr.fillvalue
         trckr.close()
-        trckr = Tracker(img, target_width, window_size, darker_target, device)    # (:105)
+        trckr = Tracker(img, target_width, window_size, darker_target, device, _fillvalue=fill)    # (:105; mode(img) again = fill)
         return trckr, ij
     trckr = Tracker(img, target_width, window_size, darker_target, device)
     ij = trckr(guess)                                           # the first frame is refined, not trusted (:95)

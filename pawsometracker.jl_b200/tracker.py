@@ -260,7 +260,9 @@ class Tracker:
     tracker with a guess runs :55-62 on the GPU, copying only the window's
     footprint of that frame."""
 
-    def __init__(self, img: np.ndarray, target_width, window_size, darker_target, device: int = 0):
+    def __init__(self, img: np.ndarray, target_width, window_size, darker_target, device: int = 0, _fillvalue=None):
+        # (_fillvalue: the mode of THIS img when the caller has just computed it — the auto-detect start builds two
+        # trackers on the same first frame, :103-105; saves a whole-frame upload and a mode pass, same value)
         if img.ndim != 2:
             raise ValueError("img must be a 2-D grayscale frame")
         self._call = None
@@ -272,8 +274,12 @@ class Tracker:
         self.darker_target = bool(darker_target)
         self._batch = TrackerBatch(1, self.sz, target_width, ws, darker_target, dtype=self.img.dtype, device=device)
         # fillvalue = mode(_img) of THIS frame, reused for all later frames (:47)
-        self._batch.set_frames([self.img])
-        self.fillvalue = int(self._batch.compute_fill()[0])
+        if _fillvalue is None:
+            self._batch.set_frames([self.img])
+            self.fillvalue = int(self._batch.compute_fill()[0])
+        else:
+            self.fillvalue = int(_fillvalue)
+            self._batch.set_fill([self.fillvalue])
         self.last_response = float("nan")
 
     @property
